@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE: generate tests/golden/*.npz from the reference.
+
+Run in the build container (where /root/reference is mounted):
+
+    python oracle/make_golden.py
+
+It imports the UNMODIFIED reference Python (oracle/ref_import.py) and records, for seeded inputs:
+
+* sscan_*.npz   -- selective_scan_ref (selective_scan_interface.py:92-158) forward + autograd grads.
+                   Input distributions follow the reference's own test
+                   (test_selective_scan.py:411-441, 474): A=-0.5*U, B,C,u,D~N(0,1), delta=0.5*U,
+                   delta_bias=0.5*U, g~N(0,1); plus cases at the model's shapes (N=16, G=4,
+                   L in {49,196}) and A=-(1..N) (MedMamba.py:357-372 init).
+* ss2d_*.npz    -- reference SS2D module (MedMamba.py:253-483) forward/backward with its state_dict.
+* vssm_tiny.npz -- reference VSSM (MedMamba.py:671-767) eval logits + train-mode grads, tiny dims.
+
+The vectors travel to the GPU box; the reference does not.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_import  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _np(t):
+    return None if t is None else t.detach().cpu().numpy()
+
+
+def sscan_case(name, batch, dim, N, L, G, has_D, has_bias, softplus, has_z=False, model_A=False,
+               bc_3d=False, with_grads=True, seed=0):
+    iface = ref_import.load_selective_scan_interface()
+    torch.manual_seed(seed)
+    if model_A:
+        A = -torch.arange(1, N + 1, dtype=torch.float32).repeat(dim, 1)
+    else:
+        A = -0.5 * torch.rand(dim, N)
+    bshape = (batch, N, L) if bc_3d else (batch, G, N, L)
+    Bm = torch.randn(*bshape)
+    Cm = torch.randn(*bshape)
+    D = torch.randn(dim) if has_D else None
+    z = torch.randn(batch, dim, L) if has_z else None
+    bias = 0.5 * torch.rand(dim) if has_bias else None
+    u = torch.randn(batch, dim, L)
+    delta = 0.5 * torch.rand(batch, dim, L)
+    g = torch.randn(batch, dim, L)
+    leaves = [t for t in (u, delta, A, Bm, Cm, D, z, bias) if t is not None]
+    for t in leaves:
+        t.requires_grad_(with_grads)
+    out, last = iface.selective_scan_ref(u, delta, A, Bm, Cm, D, z=z, delta_bias=bias,
+                                         delta_softplus=softplus, return_last_state=True)
+    rec = dict(u=_np(u), delta=_np(delta), A=_np(A), B=_np(Bm), C=_np(Cm), g=_np(g),
+               out=_np(out), last_state=_np(last), delta_softplus=np.array(int(softplus)))
+    if D is not None:
+        rec["D"] = _np(D)
+    if z is not None:
+        rec["z"] = _np(z)
+    if bias is not None:
+        rec["delta_bias"] = _np(bias)
+    if with_grads:
+        out.backward(g)
+        rec.update(du=_np(u.grad), ddelta=_np(delta.grad), dA=_np(A.grad), dB=_np(Bm.grad), dC=_np(Cm.grad))
+        if D is not None:
+            rec["dD"] = _np(D.grad)
+        if z is not None:
+            rec["dz"] = _np(z.grad)
+        if bias is not None:
+            rec["ddelta_bias"] = _np(bias.grad)
+    np.savez_compressed(os.path.join(OUT, f"sscan_{name}.npz"), **rec)
+    print("wrote", name, {k: v.shape for k, v in rec.items() if hasattr(v, "shape")})
+
+
+def ss2d_case(name, d_model, H, W, batch, seed=0):
+    mm = ref_import.load_medmamba()
+    torch.manual_seed(seed)
+    m = mm.SS2D(d_model=d_model, d_state=16)
+    # move the parameters off their structured init so that every term matters
+    with torch.no_grad():
+        m.A_logs.add_(0.3 * torch.randn_like(m.A_logs))
+        m.Ds.add_(0.5 * torch.randn_like(m.Ds))
+        m.out_norm.weight.add_(0.2 * torch.randn_like(m.out_norm.weight))
+        m.out_norm.bias.add_(0.2 * torch.randn_like(m.out_norm.bias))
+    x = torch.randn(batch, H, W, d_model, requires_grad=True)
+    g = torch.randn(batch, H, W, d_model)
+    out = m(x)
+    out.backward(g)
+    rec = {"x": _np(x), "g": _np(g), "out": _np(out), "dx": _np(x.grad)}
+    for k, v in m.state_dict().items():
+        rec["sd." + k] = _np(v)
+    for k, p in m.named_parameters():
+        rec["grad." + k] = _np(p.grad)
+    # the bare core: conv output -> 4 merged-order outputs (forward_corev0, MedMamba.py:386-424)
+    with torch.no_grad():
+        xc = torch.randn(batch, m.d_inner, H, W)
+        ys = m.forward_corev0(xc)
+        rec["core_x"] = _np(xc)
+        rec["core_y"] = _np(torch.stack(ys, 0))
+    np.savez_compressed(os.path.join(OUT, f"ss2d_{name}.npz"), **rec)
+    print("wrote ss2d", name)
+
+
+def vssm_case(seed=0):
+    mm = ref_import.load_medmamba()
+    torch.manual_seed(seed)
+    kw = dict(num_classes=6, depths=[1, 1, 1, 1], dims=[8, 16, 32, 64], drop_path_rate=0.0)
+    net = mm.VSSM(**kw)
+    x = torch.randn(4, 3, 64, 64)
+    y = torch.randint(0, 6, (4,))
+    rec = {"x": _np(x), "y": _np(y)}
+    for k, v in net.state_dict().items():
+        rec["sd." + k] = _np(v)
+    net.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = _np(net(x))
+    net.train()
+    logits = net(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    rec["logits_train"] = _np(logits)
+    rec["loss"] = _np(loss)
+    for k, p in net.named_parameters():
+        if p.grad is not None and p.numel() <= 4096:
+            rec["grad." + k] = _np(p.grad)
+    np.savez_compressed(os.path.join(OUT, "vssm_tiny.npz"), **rec)
+    print("wrote vssm_tiny loss", float(loss))
+
+
+def main():
+    assert ref_import.available(), "/root/reference is not mounted"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    # reference test-grid style (dstate=1, G in {1 (3-D B/C), 2})
+    sscan_case("grid_g1", 2, 24, 1, 64, 1, True, True, True, bc_3d=True)
+    sscan_case("grid_g2_plain", 2, 24, 1, 64, 2, False, False, False)
+    sscan_case("grid_g2_nosoftplus_bias", 2, 24, 1, 128, 2, True, True, False)
+    # the model's shapes: N=16, 4 groups, L = 7*7 and 14*14
+    sscan_case("model_L49", 2, 32, 16, 49, 4, True, True, True, model_A=True)
+    sscan_case("model_L196", 1, 32, 16, 196, 4, True, True, True)
+    # gate z, odd sizes
+    sscan_case("z_L130", 2, 16, 8, 130, 1, True, True, True, has_z=True, bc_3d=True)
+    # longer than the reference kernel's 2048-step chunk (selective_scan.cpp:307); forward only
+    sscan_case("long_L2100", 1, 8, 16, 2100, 1, True, True, True, with_grads=False)
+    ss2d_case("d8_7x5", 8, 7, 5, 2)
+    ss2d_case("d16_4x6", 16, 4, 6, 1)
+    vssm_case()
+
+
+if __name__ == "__main__":
+    main()
