@@ -1,0 +1,219 @@
+/*
+ * b200_ssm.h -- C ABI of libb200ssm.so: the B200 (sm_100a) kernels behind the reference's
+ * selective-scan / SS2D / SSD operator API.
+ *
+ * Drop-in boundary.  The reference binds its native code through the pybind11 module
+ * `selective_scan_cuda` (reference CrossMamba/FusionMamba/selective_scan/selective_scan.cpp:494-497:
+ * `fwd`, `bwd`), fed by the parameter blocks SSMParamsBase / SSMParamsBwd
+ * (selective_scan.h:26-69, 71-101: sizes, flags, raw pointers, element strides), and calls the
+ * un-vendored Triton `mamba_chunk_scan_combined` (SSD/MedSSD.py:41,361-375).  This header carries
+ * the same information as plain C: no torch types, callers allocate every output, every entry
+ * point is asynchronous on the given stream and returns 0 on success, <0 for an invalid argument
+ * (message in b200_last_error()), >0 for a cudaError_t raised by the launch.
+ *
+ * Conventions: all strides are in ELEMENTS of the tensor's dtype; the sequence (last) dimension
+ * of every activation tensor must have stride 1 (selective_scan.cpp:252-253,270-278).
+ * Thread-safety: stateless apart from a thread-local error string; re-entrant across processes
+ * (one per GPU under DDP, reference ddp_train.py:78-81).
+ */
+#ifndef B200_SSM_H_
+#define B200_SSM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream_t; /* cudaStream_t */
+
+typedef enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2 } b200_dtype;
+
+#define B200_SSCAN_MAX_DSTATE 256 /* selective_scan_common.h:11 (MAX_DSTATE) */
+#define B200_SSCAN_ROWS_PER_TASK 32
+
+/* ------------------------------------------------------------------------------------------
+ * Mamba-1 selective scan -- replaces selective_scan_cuda.fwd / .bwd
+ * (selective_scan.cpp:226-336 / 338-492; kernels selective_scan_fwd_kernel.cuh:67-303,
+ * selective_scan_bwd_kernel.cuh:75-489).
+ *
+ *   delta' = softplus?(delta + delta_bias[d])                 (x <= 20 ? log1p(exp x) : x)
+ *   x_t[n] = exp(delta'_t A[d,n]) x_{t-1}[n] + delta'_t u_t B[b,g,n,t]
+ *   out_t  = sum_n C[b,g,n,t] x_t[n] + D[d] u_t          (* silu(z_t) when z is given)
+ *
+ * Shapes: u, delta, z, out (batch, dim, L); A (dim, N) f32; B, C (batch, G, N, L) with
+ * G | dim, channel d uses group d / (dim/G); D, delta_bias (dim) f32.
+ *
+ * Two extensions serve the SS2D cross-scan (reference MedMamba.py:393-395) without materialising
+ * the four permuted copies; both default to the plain operator:
+ *   - rev_mask: bit g set => group g is scanned from t = L-1 down to 0.  Inputs are read and
+ *     outputs written at their memory position, so a reversed group consumes/produces tensors
+ *     that are NOT flipped (torch.flip of directions 2,3 becomes free).  Requires G <= 32.
+ *   - u_group_div: groups g and g' with g / u_group_div == g' / u_group_div read the same u rows
+ *     (directions k and k+2 scan the same image in opposite orders).  u is then addressed as
+ *       u + b*u_batch_stride + (g / u_group_div)*u_group_stride + r*u_row_stride,  r = d % (dim/G).
+ *     Plain operator: u_group_div = 1, u_group_stride = (dim/G)*u_row_stride.
+ *
+ * State checkpoints (replace the reference's chunk tensor `x`, selective_scan.cpp:313): the
+ * forward writes the state entering every `ckpt_every`-th step into `ckpt`, laid out
+ *   [task][chunk][n][32 rows] f32,  task = (b*G + g)*ceil((dim/G)/32) + row_tile,
+ *   chunk = 1 .. ceil(L/ckpt_every)-1   (chunk 0 is the zero state and is never stored),
+ * size from b200_sscan_ckpt_bytes().  The backward recomputes inside a chunk from its checkpoint
+ * (no per-step state is ever stored).  ckpt == NULL => inference, nothing written.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t batch, dim, seqlen, dstate, n_groups;
+    int32_t io_dtype;       /* b200_dtype of u, delta, B, C, z, out */
+    int32_t delta_softplus; /* bool */
+    uint32_t rev_mask;
+    int32_t u_group_div;
+    int32_t ckpt_every;     /* 8 or 16; ignored when ckpt == NULL */
+    int64_t u_batch_stride, u_group_stride, u_row_stride;
+    int64_t delta_batch_stride, delta_row_stride;
+    int64_t B_batch_stride, B_group_stride, B_state_stride;
+    int64_t C_batch_stride, C_group_stride, C_state_stride;
+    int64_t z_batch_stride, z_row_stride;
+    int64_t out_batch_stride, out_row_stride;
+    const void* u;
+    const void* delta;
+    const float* A;          /* (dim, N) contiguous */
+    const void* B;
+    const void* C;
+    const float* D;          /* (dim) or NULL */
+    const void* z;           /* or NULL */
+    const float* delta_bias; /* (dim) or NULL */
+    void* out;               /* (batch, dim, L) io_dtype; gated by silu(z) when z != NULL */
+    float* last_state;       /* (batch, dim, N) contiguous f32, or NULL */
+    float* ckpt;             /* see above, or NULL */
+} b200_sscan_fwd_params;
+
+typedef struct {
+    b200_sscan_fwd_params f; /* same inputs as the forward; f.out / f.last_state unused; f.ckpt required */
+    /* dout is addressed like u: dout + b*dout_batch_stride + (g / dout_group_div)*dout_group_stride
+       + r*dout_row_stride, so that the two directions that receive the same upstream gradient
+       (cross-merge adjoint) share one tensor.  Plain operator: dout_group_div = 1,
+       dout_group_stride = (dim/G)*dout_row_stride. */
+    int64_t dout_batch_stride, dout_group_stride, dout_row_stride;
+    int64_t dout_group_div;
+    int64_t du_batch_stride, du_row_stride;
+    int64_t ddelta_batch_stride, ddelta_row_stride;
+    int64_t dz_batch_stride, dz_row_stride;
+    const void* dout; /* (batch, dim, L) io_dtype */
+    void* du;         /* (batch, dim, L) io_dtype: one row per (b, d) even when u rows are shared */
+    void* ddelta;     /* (batch, dim, L) io_dtype */
+    void* dz;         /* (batch, dim, L) io_dtype, required iff f.z != NULL */
+    /* The next five are ACCUMULATED with fp32 atomics (like selective_scan.cpp:460-466):
+       the caller zero-fills them first.  dB/dC are contiguous (batch, G, N, L) f32 whatever
+       io_dtype is (selective_scan.cpp:461-462). */
+    float* dA;          /* (dim, N) */
+    float* dB;
+    float* dC;
+    float* dD;          /* (dim) or NULL */
+    float* ddelta_bias; /* (dim) or NULL */
+} b200_sscan_bwd_params;
+
+size_t b200_sscan_ckpt_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate,
+                             int32_t n_groups, int32_t ckpt_every);
+int b200_sscan_fwd(const b200_sscan_fwd_params* p, b200_stream_t stream);
+int b200_sscan_bwd(const b200_sscan_bwd_params* p, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SS2D cross-scan / cross-merge helpers (reference MedMamba.py:393-395, 420-424, 476-477).
+ *
+ * b200_cross_scan_pack:  x (batch, D, H, W)  ->  x2 (batch, 2, D, L):  x2[:,0] = x row-major,
+ *   x2[:,1] = x transposed (column-major order).  With rev_mask = 0b1100 and u_group_div = 1 on a
+ *   direction order (hw, wh, hw-reversed, wh-reversed) this is all the data movement the four
+ *   directions need.
+ * b200_cross_merge:  ys (batch, 4, D, L) as written by the scan with rev_mask (every direction at
+ *   its memory position)  ->  y (batch, L, D) = ys0 + ys2 + transpose(ys1 + ys3), i.e. the sum of
+ *   the four un-permuted directions laid out (B, H, W, D).
+ * b200_cross_merge_bwd: dy (batch, L, D) -> dys2 (batch, 2, D, L) (the adjoint scatter): [0] feeds
+ *   directions 0 and 1, [1] (column-major planes) feeds directions 2 and 3 (dout_group_div = 2).
+ * ------------------------------------------------------------------------------------------ */
+int b200_cross_scan_pack(const void* x, void* x2, int32_t batch, int32_t D, int32_t H, int32_t W,
+                         int32_t dtype, b200_stream_t stream);
+int b200_cross_scan_pack_bwd(const void* dx2, void* dx, int32_t batch, int32_t D, int32_t H, int32_t W,
+                             int32_t dtype, b200_stream_t stream);
+int b200_cross_merge(const void* ys, void* y, int32_t batch, int32_t D, int32_t H, int32_t W,
+                     int32_t dtype, b200_stream_t stream);
+int b200_cross_merge_bwd(const void* dy, void* dys, int32_t batch, int32_t D, int32_t H, int32_t W,
+                         int32_t dtype, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mamba-2 SSD -- replaces mamba_ssm.ops.triton.ssd_combined.mamba_chunk_scan_combined
+ * (call contract: reference SSD/MedSSD.py:344-375).
+ *
+ *   dt'   = clamp(softplus?(dt + dt_bias[h]), dt_min, dt_max)
+ *   S_t   = exp(dt'_t A[h]) S_{t-1} + dt'_t x_t (outer) B_t        S: (P, N) per (batch, head)
+ *   y_t   = S_t C_t + D[h] x_t                                    (* silu(z_t) when z is given)
+ *
+ * x, z, out (batch, L, H, P); dt (batch, L, H); B, C (batch, L, G, N); A, D, dt_bias (H) f32.
+ * Every tensor is addressed by explicit element strides (the reference passes permuted views
+ * whose L stride is 1).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t batch, seqlen, nheads, headdim, n_groups, dstate, chunk_size;
+    int32_t io_dtype; /* x, dt, B, C, z, out */
+    int32_t dt_softplus;
+    int32_t D_has_hdim;
+    float dt_min, dt_max;
+    int64_t x_stride[4];   /* batch, L, head, p */
+    int64_t dt_stride[3];  /* batch, L, head */
+    int64_t B_stride[4];   /* batch, L, group, n */
+    int64_t C_stride[4];
+    int64_t z_stride[4];
+    int64_t out_stride[4];
+    const void* x;
+    const void* dt;
+    const float* A;
+    const void* B;
+    const void* C;
+    const float* D;       /* (H) or (H, P), or NULL */
+    const void* z;        /* or NULL */
+    const float* dt_bias; /* or NULL */
+    const float* initial_states; /* (batch, H, P, N) contiguous f32 or NULL */
+    void* out;
+    float* final_states;  /* (batch, H, P, N) contiguous f32 or NULL */
+    void* workspace;      /* b200_ssd_workspace_bytes() bytes: chunk states + decay tables kept for backward */
+} b200_ssd_fwd_params;
+
+typedef struct {
+    b200_ssd_fwd_params f;
+    int64_t dout_stride[4];
+    const void* dout;
+    /* all gradients are contiguous fp32 in the logical shapes of their primals */
+    float* dx;       /* (batch, L, H, P) */
+    float* ddt;      /* (batch, L, H) */
+    float* dB;       /* (batch, L, G, N)  (accumulated: caller zero-fills) */
+    float* dC;       /* (batch, L, G, N)  (accumulated: caller zero-fills) */
+    float* dA;       /* (H)   (accumulated: caller zero-fills) */
+    float* dD;       /* (H) or (H, P) or NULL (accumulated) */
+    float* ddt_bias; /* (H) or NULL (accumulated) */
+    float* dz;       /* (batch, L, H, P) or NULL */
+} b200_ssd_bwd_params;
+
+size_t b200_ssd_workspace_bytes(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim,
+                                int32_t dstate, int32_t chunk_size);
+int b200_ssd_fwd(const b200_ssd_fwd_params* p, b200_stream_t stream);
+int b200_ssd_bwd(const b200_ssd_bwd_params* p, b200_stream_t stream);
+
+/* Gated RMSNorm used by SS2D_with_SSD (reference SSD/MedSSD.py:268-269,393-394;
+ * mamba_ssm.ops.triton.layernorm_gated.RMSNorm with norm_before_gate=False, one group):
+ *   y = rmsnorm(x * silu(z)) * w,   rows of length `dim`, fp32.  rstd (rows) is kept for backward. */
+int b200_rmsnorm_gated_fwd(const float* x, const float* z, const float* w, float* y, float* rstd,
+                           int64_t rows, int32_t dim, float eps, b200_stream_t stream);
+int b200_rmsnorm_gated_bwd(const float* x, const float* z, const float* w, const float* rstd,
+                           const float* dy, float* dx, float* dz, float* dw_partial /* (grid, dim) */,
+                           int32_t dw_rows, int64_t rows, int32_t dim, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------ */
+const char* b200_last_error(void);   /* thread-local message of the last failing call */
+int b200_version(void);              /* ABI version, bumped on any struct change */
+int b200_kernel_launches(void);      /* number of kernels this library has launched in this process */
+size_t b200_sizeof_params(int32_t which); /* 0 sscan_fwd, 1 sscan_bwd, 2 ssd_fwd, 3 ssd_bwd: lets a binding check its struct layout */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_SSM_H_ */

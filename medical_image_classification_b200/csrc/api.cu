@@ -1,0 +1,45 @@
+// api.cu -- error plumbing and ABI bookkeeping of libb200ssm.so (see include/b200_ssm.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+    count_launch(1);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+}  // namespace b200
+
+extern "C" const char* b200_last_error(void) { return b200::g_err; }
+extern "C" int b200_version(void) { return 1; }
+extern "C" int b200_kernel_launches(void) { return b200::g_launches.load(std::memory_order_relaxed); }
+extern "C" size_t b200_sizeof_params(int32_t which) {
+    switch (which) {
+        case 0: return sizeof(b200_sscan_fwd_params);
+        case 1: return sizeof(b200_sscan_bwd_params);
+        case 2: return sizeof(b200_ssd_fwd_params);
+        case 3: return sizeof(b200_ssd_bwd_params);
+        default: return 0;
+    }
+}
