@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- MedMamba-T training throughput on B200 (BASELINE.json metric) + selective-scan roofline.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (port)
+
+A "step" is one training step (forward, CrossEntropy, backward, Adam) of MedMamba-T
+(MedMamba.py VSSM, depths 2-2-4-2, dims 96-768, 6 classes) on synthetic 3x224x224 images,
+batch 64 per GPU, bf16 autocast (BASELINE.json configs[1]); N > 1 = ddp_train.py-style data
+parallelism (one process per GPU, NCCL gradient all-reduce overlapped with backward).
+
+One JSON line on rank 0:
+  value      images/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric with the step's input copied from pinned host memory and the loss read
+             back to the host inside the timed region
+  roofline   dominant libb200ssm kernel (selective scan): algorithmic bytes (SURVEY.md 8d formula)
+             / CUDA-event time per launch, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's CPU data flow (oracle/cpu_path.py: PyTorch CPU ops + the C
+             restatement of selective_scan_ref) on a bounded sample, rank 0, N=1
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MedMamba-T train images/sec @224"
+UNIT = "images/s"
+PER_GPU_BATCH = 64
+NUM_CLASSES = 6
+WORKLOAD = ("MedMamba-T (VSSM depths 2-2-4-2, dims 96-768, 6 classes) bf16-autocast training step, "
+            "batch 64 per GPU, synthetic 3x224x224 (BASELINE.json configs[1])")
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi's numbers through NVML)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int, period: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-launch CUDA-event timing of the libb200ssm selective-scan kernels
+# ------------------------------------------------------------------------------------------------
+class ScanProfiler:
+    """Wraps selective_scan_interface.launch_fwd/launch_bwd with torch.cuda events on the stream the
+    kernels are launched on (torch's current stream), and records the algorithmic bytes per launch."""
+
+    def __init__(self):
+        import torch
+        from medical_image_classification_b200 import selective_scan_interface as ssi
+        self.torch, self.ssi = torch, ssi
+        self.records = []  # (key, bytes, start_event, end_event)
+        self.enabled = False
+
+    @staticmethod
+    def algorithmic_bytes(kind, u, delta, Bm):
+        """s = bytes per I/O element, E = B*KD*L, Ebc = B*K*N*L.
+        fwd: s*(3E + 2Ebc) + 4*(KD*N + 2KD);  bwd: s*(5E + 2Ebc) + 4*2Ebc + 4*(2KD*N + 4KD)."""
+        s = u.element_size()
+        batch, KD, L = delta.shape
+        G, N = Bm.shape[1], Bm.shape[2]
+        E, Ebc = batch * KD * L, batch * G * N * L
+        if kind == "fwd":
+            return s * (3 * E + 2 * Ebc) + 4 * (KD * N + 2 * KD)
+        return s * (5 * E + 2 * Ebc) + 4 * 2 * Ebc + 4 * (2 * KD * N + 4 * KD)
+
+    def install(self):
+        self.ssi.set_profiler(self)
+
+    def begin(self):
+        if not self.enabled:
+            return None
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def end(self, e0, kind, u, delta, Bm):
+        if e0 is None:
+            return
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e1.record()
+        key = (kind, tuple(delta.shape), Bm.shape[2], str(u.dtype))
+        self.records.append((key, self.algorithmic_bytes(kind, u, delta, Bm), e0, e1))
+
+    def summary(self, peak_gbs, peak_src, steps):
+        """Per (kernel, shape): launches, mean ms between events recorded immediately around the
+        C-ABI launch on the launching stream, achieved GB/s."""
+        agg = {}
+        for key, nbytes, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            a = agg.setdefault(key, [0, 0.0, nbytes])
+            a[0] += 1
+            a[1] += ms
+        if not agg:
+            return None, None
+        rows = []
+        for key, (n, ms, nbytes) in agg.items():
+            rows.append({"kernel": f"sscan_{key[0]}_kernel", "shape_b_kd_l": list(key[1]), "dstate": key[2],
+                         "io": key[3].replace("torch.", ""), "launches": n, "ms_per_launch": ms / n,
+                         "bytes_per_launch": nbytes, "gbs": nbytes / (ms / n) / 1e6})
+        rows.sort(key=lambda r: -r["ms_per_launch"] * r["launches"])
+        top = rows[0]
+        tot_bytes = sum(r["bytes_per_launch"] * r["launches"] for r in rows)
+        tot_ms = sum(r["ms_per_launch"] * r["launches"] for r in rows)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+                traffic = json.load(fh).get(top["kernel"] + ":" + "x".join(map(str, top["shape_b_kd_l"])))
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": top["kernel"], "shape_b_kd_l": top["shape_b_kd_l"],
+                "achieved": round(top["gbs"], 1), "peak": peak_gbs, "unit": "GB/s",
+                "frac": round(top["gbs"] / peak_gbs, 4), "traffic": traffic,
+                "bytes_per_launch": top["bytes_per_launch"], "ms_per_launch": round(top["ms_per_launch"], 4),
+                "peak_source": peak_src, "formula": "SURVEY.md 8(d) API-boundary bytes, fp32 I/O (s=4)"}
+        allscan = {"launches_per_step": round(sum(r["launches"] for r in rows) / steps, 1),
+                   "bytes_per_step": tot_bytes / steps, "ms_per_step": round(tot_ms / steps, 4),
+                   "achieved": round(tot_bytes / tot_ms / 1e6, 1), "unit": "GB/s",
+                   "frac": round(tot_bytes / tot_ms / 1e6 / peak_gbs, 4),
+                   "per_kernel": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rows]}
+        return roof, allscan
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's CPU data flow (port)
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_time(batch: int, steps: int = 1, warmup: int = 0, threads: int | None = None):
+    import torch
+    import oracle
+    from oracle.cpu_path import bind_cpu_core
+    from medical_image_classification_b200.models import medmamba_t
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = medmamba_t(num_classes=NUM_CLASSES)
+    bind_cpu_core(net)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    x = torch.randn(batch, 3, 224, 224)
+    y = torch.randint(0, NUM_CLASSES, (batch,))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(net(x), y)
+        loss.backward()
+        opt.step()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), max(threads, oracle.threads())
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host
+    threads, each step a bounded sample (a small batch) of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    t1, threads = cpu_train_step_time(1, steps=1, warmup=0)          # calibration
+    budget = 150.0
+    n_steps = args.steps + args.warmup
+    b = int(max(1, min(8, budget / max(n_steps, 1) / max(t1, 1e-3))))
+    t, threads = cpu_train_step_time(b, steps=args.steps, warmup=args.warmup)
+    value = b / t
+    sample = (f"MedMamba-T fp32 fwd+bwd+Adam on batch {b} of synthetic 3x224x224 per step "
+              f"(PyTorch CPU ops + C/OpenMP restatement of selective_scan_ref), {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "host_cores": cores},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from medical_image_classification_b200 import _lib
+    from medical_image_classification_b200.models import medmamba_t
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ddp = world > 1
+    if ddp:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(1234 + rank)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t, threads = cpu_train_step_time(args.cpu_batch, steps=1, warmup=0)
+        cpu_base = {"value": round(args.cpu_batch / t, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"one fp32 MedMamba-T training step (fwd+bwd+Adam) on batch {args.cpu_batch} of synthetic "
+                              f"3x224x224 (BASELINE.json configs[0]); PyTorch CPU ops + C/OpenMP restatement of "
+                              f"selective_scan_ref; {t:.1f} s",
+                    "host_cores": os.cpu_count()}
+
+    net = medmamba_t(num_classes=NUM_CLASSES).to(dev)
+    if ddp:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+    else:
+        model = net
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    B = args.batch
+    x_dev = torch.randn(B, 3, 224, 224, device=dev)
+    y_dev = torch.randint(0, NUM_CLASSES, (B,), device=dev)
+    x_host = torch.randn(B, 3, 224, 224).pin_memory()
+    y_host = torch.randint(0, NUM_CLASSES, (B,)).pin_memory()
+
+    def step(x, y):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(model(x).float(), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if ddp:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    prof = ScanProfiler()
+    prof.install()
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- timed region 1: inputs resident in HBM ----
+    prof.enabled = True
+    launches0 = _lib.launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    launches = _lib.launches() - launches0
+    prof.enabled = False
+    ms = e0.elapsed_time(e1)
+    # ---- timed region 2: end to end (pinned host input -> device, loss -> host) ----
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        xb = x_host.to(dev, non_blocking=True)
+        yb = y_host.to(dev, non_blocking=True)
+        last = step(xb, yb).item()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop()
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if ddp:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        peak, peak_src = peaks()
+        roof, allscan = prof.summary(peak, peak_src, args.steps)
+        total = B * world * args.steps
+        line = {"metric": METRIC, "value": round(total / (ms / 1e3), 2), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
+                           "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-4 (fused)",
+                           "scan_io": "fp32 (as the reference calls it), fp32 state",
+                           "l2": "per-step activations (> 10 GB) exceed the 126 MB L2; no explicit flush"},
+                "e2e": {"value": round(total / (ms_e2e / 1e3), 2), "unit": UNIT,
+                        "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
+                        "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": round(last, 4)},
+                "gpu_launches": launches, "roofline": roof, "scan_fwd_bwd": allscan, "clocks": clocks}
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if ddp:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 64)")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,170 @@
+"""MedMamba (VSSM) classifier built on the B200 SS2D block -- module tree and parameter names follow
+the reference `MedMamba.py` (PatchEmbed2D :146-169, PatchMerging2D :172-212, channel_shuffle
+:486-499, SS_Conv_SSM :502-538, VSSLayer :541-604, VSSM :671-767) so that a reference state_dict
+loads with strict=True.  MedMamba-T = VSSM(depths=[2,2,4,2], dims=[96,192,384,768]) (defaults).
+
+This file is host-side glue around the hot path (ss2d.SS2D); convolutions, linears and norms stay
+on cuDNN/cuBLAS exactly as in the reference.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from .ss2d import SS2D
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (the reference takes it from timm)."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = float(drop_prob)
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask.div_(keep)
+
+    def extra_repr(self):
+        return f"drop_prob={self.drop_prob}"
+
+
+class PatchEmbed2D(nn.Module):
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None, **kwargs):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+    def forward(self, x):
+        x = self.proj(x).permute(0, 2, 3, 1)
+        return self.norm(x) if self.norm is not None else x
+
+
+class PatchMerging2D(nn.Module):
+    """2x2 patch merge: (B, H, W, C) -> (B, H/2, W/2, 2C)."""
+
+    def __init__(self, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+    def forward(self, x):
+        B, H, W, C = x.shape
+        h2, w2 = H // 2, W // 2
+        parts = [x[:, i::2, j::2, :][:, :h2, :w2, :] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))]
+        x = torch.cat(parts, dim=-1)
+        return self.reduction(self.norm(x))
+
+
+def channel_shuffle(x, groups: int):
+    B, H, W, C = x.shape
+    return x.view(B, H, W, groups, C // groups).transpose(3, 4).reshape(B, H, W, C)
+
+
+class SS_Conv_SSM(nn.Module):
+    """Two-branch block: half the channels through conv3x3-conv3x3-conv1x1, half through
+    LayerNorm -> SS2D; concat, channel shuffle, residual."""
+
+    def __init__(self, hidden_dim=0, drop_path=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                 attn_drop_rate=0.0, d_state=16, **kwargs):
+        super().__init__()
+        c = hidden_dim // 2
+        self.ln_1 = norm_layer(c)
+        self.self_attention = SS2D(d_model=c, dropout=attn_drop_rate, d_state=d_state, **kwargs)
+        self.drop_path = DropPath(drop_path)
+        self.conv33conv33conv11 = nn.Sequential(
+            nn.BatchNorm2d(c),
+            nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1),
+            nn.BatchNorm2d(c),
+            nn.ReLU(),
+            nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1),
+            nn.BatchNorm2d(c),
+            nn.ReLU(),
+            nn.Conv2d(c, c, kernel_size=1, stride=1),
+            nn.ReLU(),
+        )
+
+    def forward(self, input):
+        left, right = input.chunk(2, dim=-1)
+        x = self.drop_path(self.self_attention(self.ln_1(right)))
+        left = self.conv33conv33conv11(left.permute(0, 3, 1, 2).contiguous())
+        left = left.permute(0, 2, 3, 1)
+        out = channel_shuffle(torch.cat((left, x.to(left.dtype)), dim=-1), groups=2)
+        return out + input
+
+
+class VSSLayer(nn.Module):
+    def __init__(self, dim, depth, attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, downsample=None,
+                 use_checkpoint=False, d_state=16, **kwargs):
+        super().__init__()
+        self.dim = dim
+        self.use_checkpoint = use_checkpoint
+        self.blocks = nn.ModuleList([
+            SS_Conv_SSM(hidden_dim=dim, drop_path=drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
+                        norm_layer=norm_layer, attn_drop_rate=attn_drop, d_state=d_state)
+            for i in range(depth)])
+        self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = torch.utils.checkpoint.checkpoint(blk, x, use_reentrant=False) if self.use_checkpoint else blk(x)
+        return self.downsample(x) if self.downsample is not None else x
+
+
+class VSSM(nn.Module):
+    def __init__(self, patch_size=4, in_chans=3, num_classes=1000, depths=(2, 2, 4, 2), dims=(96, 192, 384, 768),
+                 d_state=16, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=nn.LayerNorm,
+                 patch_norm=True, use_checkpoint=False, **kwargs):
+        super().__init__()
+        depths, n = list(depths), len(depths)
+        dims = [int(dims * 2 ** i) for i in range(n)] if isinstance(dims, int) else list(dims)
+        self.num_classes, self.num_layers = num_classes, n
+        self.embed_dim, self.num_features, self.dims = dims[0], dims[-1], dims
+        self.patch_embed = PatchEmbed2D(patch_size=patch_size, in_chans=in_chans, embed_dim=dims[0],
+                                        norm_layer=norm_layer if patch_norm else None)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = torch.linspace(0, drop_path_rate, sum(depths)).tolist()
+        self.layers = nn.ModuleList()
+        for i in range(n):
+            self.layers.append(VSSLayer(
+                dim=dims[i], depth=depths[i], d_state=d_state, attn_drop=attn_drop_rate,
+                drop_path=dpr[sum(depths[:i]):sum(depths[:i + 1])], norm_layer=norm_layer,
+                downsample=PatchMerging2D if i < n - 1 else None, use_checkpoint=use_checkpoint))
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
+        self.apply(self._init_weights)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02, a=-2.0, b=2.0)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    def forward_backbone(self, x):
+        x = self.pos_drop(self.patch_embed(x))
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+    def forward(self, x):
+        x = self.forward_backbone(x)
+        x = self.avgpool(x.permute(0, 3, 1, 2)).flatten(1)
+        return self.head(x)
+
+
+def medmamba_t(num_classes=6, **kw):
+    """MedMamba-T, the configuration BASELINE.json names (depths 2-2-4-2, dims 96-768)."""
+    return VSSM(num_classes=num_classes, depths=[2, 2, 4, 2], dims=[96, 192, 384, 768], **kw)

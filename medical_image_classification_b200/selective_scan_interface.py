@@ -25,6 +25,15 @@ from . import _lib
 
 CKPT_EVERY = 8  # steps between state checkpoints written by the forward for the recompute backward
 
+# Optional per-launch profiler (bench.py): an object with begin() -> token and
+# end(token, kind, u, delta, Bm), called immediately around the C-ABI launch on the current stream.
+_profiler = None
+
+
+def set_profiler(p) -> None:
+    global _profiler
+    _profiler = p
+
 
 def _last_contig(t):
     return t if t is None or t.stride(-1) == 1 else t.contiguous()
@@ -96,8 +105,12 @@ def launch_fwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, rev_mask=0
     p.ckpt_every = CKPT_EVERY
     p.out_batch_stride, p.out_row_stride = out.stride(0), out.stride(1)
     p.out, p.last_state, p.ckpt = out.data_ptr(), _lib.ptr(last_state), _lib.ptr(ckpt)
+    prof = _profiler
     with torch.cuda.device(u.device):
+        tok = prof.begin() if prof is not None else None
         _lib.check(lib.b200_sscan_fwd(C.byref(p), _lib.stream_ptr(u.device)), "b200_sscan_fwd")
+        if prof is not None:
+            prof.end(tok, "fwd", u, delta, Bm)
     return out, last_state, ckpt
 
 
@@ -131,8 +144,12 @@ def launch_bwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, ckpt, dout
         q.dz_batch_stride, q.dz_row_stride = dz.stride(0), dz.stride(1)
     q.dout, q.du, q.ddelta, q.dz = dout.data_ptr(), du.data_ptr(), ddelta.data_ptr(), _lib.ptr(dz)
     q.dA, q.dB, q.dC, q.dD, q.ddelta_bias = dA.data_ptr(), dB.data_ptr(), dC.data_ptr(), _lib.ptr(dD), _lib.ptr(dbias)
+    prof = _profiler
     with torch.cuda.device(dev):
+        tok = prof.begin() if prof is not None else None
         _lib.check(lib.b200_sscan_bwd(C.byref(q), _lib.stream_ptr(dev)), "b200_sscan_bwd")
+        if prof is not None:
+            prof.end(tok, "bwd", u, delta, Bm)
     return du, ddelta, dA, dB, dC, dD, dbias, dz
 
 

@@ -1,0 +1,137 @@
+"""SS2D block (Mamba-1 four-direction 2-D selective scan) -- B200 mirror of the reference module
+`SS2D` (reference MedMamba.py:253-483): same constructor arguments, same parameter names and shapes
+(`in_proj.weight, conv2d.{weight,bias}, x_proj_weight (4,R+2N,D), dt_projs_weight (4,D,R),
+dt_projs_bias (4,D), A_logs (4D,N), Ds (4D), out_norm.{weight,bias}, out_proj.weight`), so reference
+checkpoints load with strict=True, and the same `forward((B,H,W,C)) -> (B,H,W,C)`.
+
+What differs is how `forward_core` moves data (cross.py / csrc/sscan.cu / csrc/cross.cu): the four
+permuted copies of the image, the flips and the four-way un-permute of the reference
+(MedMamba.py:393-395, 420-424, 476-477) are replaced by one pack kernel, a scan kernel that walks
+two of the directions backwards, and one merge kernel.  The x_proj / dt_proj contractions
+(MedMamba.py:397-400) are point-wise in the sequence position, so they run on the un-permuted
+[x, x^T] pair as plain batched GEMMs (cuBLAS).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .cross import DIR_PERM, cross_scan_pack, scan_merge
+from .selective_scan_interface import selective_scan_fn
+
+
+class SS2D(nn.Module):
+    def __init__(self, d_model, d_state=16, d_conv=3, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
+                 dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, dropout=0.0, conv_bias=True, bias=False,
+                 device=None, dtype=None, **kwargs):
+        fk = {"device": device, "dtype": dtype}
+        super().__init__()
+        self.d_model = d_model
+        self.d_state = d_state
+        self.d_conv = d_conv
+        self.expand = expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        K, D, N, R = 4, self.d_inner, d_state, self.dt_rank
+
+        self.in_proj = nn.Linear(d_model, 2 * D, bias=bias, **fk)
+        self.conv2d = nn.Conv2d(D, D, kernel_size=d_conv, padding=(d_conv - 1) // 2, groups=D, bias=conv_bias, **fk)
+        self.act = nn.SiLU()
+
+        # per-direction projections, stacked (MedMamba.py:296-317)
+        bound = 1.0 / math.sqrt(D)
+        self.x_proj_weight = nn.Parameter(torch.empty(K, R + 2 * N, D, **fk).uniform_(-bound, bound))
+        std = R ** -0.5 * dt_scale
+        w = torch.empty(K, D, R, **fk)
+        if dt_init == "constant":
+            w.fill_(std)
+        elif dt_init == "random":
+            w.uniform_(-std, std)
+        else:
+            raise NotImplementedError(dt_init)
+        self.dt_projs_weight = nn.Parameter(w)
+        # bias such that softplus(bias) is log-uniform in [dt_min, dt_max] (MedMamba.py:343-351)
+        dt = torch.exp(torch.rand(K, D, **fk) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min))
+        dt = dt.clamp(min=dt_init_floor)
+        self.dt_projs_bias = nn.Parameter(dt + torch.log(-torch.expm1(-dt)))
+        self.dt_projs_bias._no_reinit = True
+
+        # S4D-real A = -(1..N) per channel and direction; D = 1 (MedMamba.py:357-384)
+        A = torch.arange(1, N + 1, dtype=torch.float32, device=device).repeat(K * D, 1)
+        self.A_logs = nn.Parameter(torch.log(A))
+        self.A_logs._no_weight_decay = True
+        self.Ds = nn.Parameter(torch.ones(K * D, device=device))
+        self.Ds._no_weight_decay = True
+
+        self.out_norm = nn.LayerNorm(D)
+        self.out_proj = nn.Linear(D, d_model, bias=bias, **fk)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else None
+        self.forward_core = self.forward_core_fused
+
+    # ---- the hot path --------------------------------------------------------------------------
+    def _dir_params(self):
+        """Per-direction parameters re-ordered to the internal direction order (cross.DIR_PERM)."""
+        K, D, N = 4, self.d_inner, self.d_state
+        perm = list(DIR_PERM)
+        Wx = self.x_proj_weight.float()[perm]                       # (4, R+2N, D)
+        Wdt = self.dt_projs_weight.float()[perm]                    # (4, D, R)
+        bias = self.dt_projs_bias.float()[perm].reshape(-1)         # (4D)
+        As = -torch.exp(self.A_logs.float()).view(K, D, N)[perm].reshape(K * D, N)
+        Ds = self.Ds.float().view(K, D)[perm].reshape(-1)
+        return Wx, Wdt, bias, As, Ds
+
+    def forward_core_fused(self, x: torch.Tensor):
+        """x (B, D, H, W) -> merged y (B, H, W, D) fp32 == y1+y2+y3+y4 of the reference's
+        forward_corev0 (MedMamba.py:386-424) already transposed to channels-last (:476-477)."""
+        B, D, H, W = x.shape
+        L = H * W
+        R, N = self.dt_rank, self.d_state
+        with torch.autocast("cuda", enabled=False):
+            x2 = cross_scan_pack(x.float())                         # (B, 2, D, L)
+            Wx, Wdt, bias, As, Ds = self._dir_params()
+            # directions (0,1) read x2[:,0], (2,3) read x2[:,1]: one GEMM per layout
+            x_dbl = torch.matmul(Wx.reshape(2, 2 * (R + 2 * N), D).unsqueeze(0), x2)   # (B, 2, 2C, L)
+            x_dbl = x_dbl.view(B, 4, R + 2 * N, L)
+            dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+            dts = torch.matmul(Wdt.unsqueeze(0), dts_r)              # (B, 4, D, L)
+            y = scan_merge(x2, dts.view(B, 4 * D, L), As, Bs, Cs, Ds, bias, H, W)      # (B, L, D)
+        return y.view(B, H, W, D)
+
+    def forward_core_api(self, x: torch.Tensor):
+        """The reference's data flow verbatim (four materialised directions, operator-API call,
+        flips and transposes), kept for parity tests of `selective_scan_fn` inside the module."""
+        B, D, H, W = x.shape
+        L = H * W
+        K = 4
+        x_hwwh = torch.stack([x.view(B, -1, L), x.transpose(2, 3).contiguous().view(B, -1, L)], dim=1)
+        xs = torch.cat([x_hwwh, x_hwwh.flip(-1)], dim=1)
+        x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, self.x_proj_weight)
+        dts, Bs, Cs = torch.split(x_dbl, [self.dt_rank, self.d_state, self.d_state], dim=2)
+        dts = torch.einsum("bkrl,kdr->bkdl", dts, self.dt_projs_weight)
+        out_y = selective_scan_fn(
+            xs.float().view(B, -1, L), dts.contiguous().float().view(B, -1, L),
+            -torch.exp(self.A_logs.float()), Bs.float(), Cs.float(), self.Ds.float(), z=None,
+            delta_bias=self.dt_projs_bias.float().view(-1), delta_softplus=True).view(B, K, -1, L)
+        inv_y = out_y[:, 2:4].flip(-1)
+        wh_y = out_y[:, 1].view(B, -1, W, H).transpose(2, 3).contiguous().view(B, -1, L)
+        invwh_y = inv_y[:, 1].view(B, -1, W, H).transpose(2, 3).contiguous().view(B, -1, L)
+        y = out_y[:, 0] + inv_y[:, 0] + wh_y + invwh_y
+        return y.transpose(1, 2).contiguous().view(B, H, W, -1)
+
+    def forward(self, x: torch.Tensor, **kwargs):
+        B, H, W, C = x.shape
+        xz = self.in_proj(x)
+        x, z = xz.chunk(2, dim=-1)
+        x = x.permute(0, 3, 1, 2).contiguous()
+        x = self.act(self.conv2d(x))
+        y = self.forward_core(x)                                    # (B, H, W, D) fp32
+        assert y.dtype == torch.float32
+        y = self.out_norm(y)
+        y = y * F.silu(z)
+        out = self.out_proj(y)
+        if self.dropout is not None:
+            out = self.dropout(out)
+        return out

@@ -32,7 +32,7 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 
 def _np(t):
-    return None if t is None else t.detach().cpu().numpy()
+    return None if t is None else t.detach().cpu().numpy().copy()  # copy: BN buffers are updated in place later
 
 
 def sscan_case(name, batch, dim, N, L, G, has_D, has_bias, softplus, has_z=False, model_A=False,

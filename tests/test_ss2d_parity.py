@@ -1,0 +1,126 @@
+"""GPU parity of the SS2D hot path (cross-scan -> selective scan -> cross-merge) and of the
+module/model mirrors against vectors generated from the UNMODIFIED reference modules
+(tests/golden/ss2d_*.npz, vssm_tiny.npz; oracle/make_golden.py) and the numpy index-map oracle
+(oracle.cross_scan_ref / cross_merge_ref, restating MedMamba.py:393-395, 420-424, 476-477)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+from medical_image_classification_b200 import cross  # noqa: E402
+from medical_image_classification_b200.models import VSSM  # noqa: E402
+from medical_image_classification_b200.ss2d import SS2D  # noqa: E402
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu().numpy() if hasattr(a, "detach") else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 7, 5), (1, 33, 14, 14), (2, 40, 56, 56), (1, 3, 9, 40)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cross_scan_pack_is_bit_exact(shape, dtype):
+    torch.manual_seed(0)
+    x = torch.randn(*shape, device="cuda").to(dtype).requires_grad_()
+    x2 = cross.cross_scan_pack(x)
+    ref = oracle.cross_scan_ref(x.detach().float().cpu().numpy())[:, :2]     # k=0 (hw), k=1 (wh)
+    assert np.array_equal(x2.detach().float().cpu().numpy(), ref)
+    g = torch.randn_like(x2)
+    x2.backward(g)
+    B, D, H, W = shape
+    gref = g[:, 0].float().view(B, D, H, W) + g[:, 1].float().view(B, D, W, H).transpose(2, 3)
+    assert torch.equal(x.grad, gref.to(dtype))
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 7, 5), (1, 33, 14, 14), (2, 40, 56, 56), (1, 3, 9, 40)])
+def test_cross_merge_matches_index_oracle(shape):
+    """ys in the internal direction order with reversed directions stored at memory positions ==
+    the reference's scan-order ys with k=2,3 flipped."""
+    B, D, H, W = shape
+    L = H * W
+    torch.manual_seed(1)
+    ys_ref = torch.randn(B, 4, D, L)                         # reference: scan order, k = 0..3
+    mem = ys_ref.clone()
+    mem[:, 2:4] = ys_ref[:, 2:4].flip(-1)                    # reversed directions at memory positions
+    internal = mem[:, list(cross.DIR_PERM)].cuda().requires_grad_()
+    y = cross.cross_merge(internal, H, W)
+    ref = oracle.cross_merge_ref(ys_ref.numpy(), H, W).reshape(B, L, D)
+    assert relerr(y, ref) < 1e-6
+    g = torch.randn_like(y)
+    y.backward(g)
+    # adjoint: every direction receives dy at its own positions
+    gy = g.cpu().view(B, H, W, D).permute(0, 3, 1, 2)        # (B, D, H, W)
+    exp_hw = gy.reshape(B, D, L)
+    exp_wh = gy.transpose(2, 3).reshape(B, D, L)
+    got = internal.grad.cpu()
+    assert torch.equal(got[:, 0], exp_hw) and torch.equal(got[:, 1], exp_hw)
+    assert torch.equal(got[:, 2], exp_wh) and torch.equal(got[:, 3], exp_wh)
+
+
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "ss2d_*.npz")))
+
+
+def load_module(g):
+    sd = {k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd.")}
+    d_model = sd["in_proj.weight"].shape[1]
+    m = SS2D(d_model=d_model, d_state=16)
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[5:-4] for p in CASES])
+@pytest.mark.parametrize("core", ["fused", "api"])
+def test_ss2d_module_matches_reference(path, core):
+    g = np.load(path)
+    m = load_module(g)
+    if core == "api":
+        m.forward_core = m.forward_core_api
+    # bare core: conv output -> merged output
+    xc = torch.tensor(g["core_x"]).cuda()
+    y = m.forward_core(xc)
+    B, D, H, W = xc.shape
+    core_ref = torch.tensor(g["core_y"]).sum(0).transpose(1, 2).reshape(B, H, W, D)   # y1+y2+y3+y4, (B,H,W,D)
+    assert relerr(y, core_ref.numpy()) < 1e-5
+    # whole module forward + backward
+    x = torch.tensor(g["x"]).cuda().requires_grad_()
+    out = m(x)
+    assert relerr(out, g["out"]) < 2e-5
+    out.backward(torch.tensor(g["g"]).cuda())
+    assert relerr(x.grad, g["dx"]) < 5e-5
+    for k, p in m.named_parameters():
+        assert relerr(p.grad, g["grad." + k]) < 1e-4, k
+
+
+def test_vssm_tiny_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "vssm_tiny.npz"))
+    net = VSSM(num_classes=6, depths=[1, 1, 1, 1], dims=[8, 16, 32, 64], drop_path_rate=0.0)
+    net.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    net = net.cuda()
+    x = torch.tensor(g["x"]).cuda()
+    y = torch.tensor(g["y"]).cuda()
+    net.eval()
+    with torch.no_grad():
+        logits = net(x)
+    assert relerr(logits, g["logits_eval"]) < 1e-4
+    assert torch.equal(logits.argmax(-1).cpu(), torch.tensor(g["logits_eval"]).argmax(-1))   # equal top-1
+    net.train()
+    out = net(x)
+    loss = torch.nn.functional.cross_entropy(out, y)
+    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    loss.backward()
+    checked = 0
+    for k, p in net.named_parameters():
+        if "grad." + k in g.files:
+            ref = g["grad." + k]
+            if np.abs(ref).max() > 1e-7:
+                assert relerr(p.grad, ref) < 2e-3, k
+                checked += 1
+    assert checked > 20

@@ -57,7 +57,7 @@ def test_golden_fp32(path):
     assert res["out"].dtype == torch.float32
     assert relerr(res["out"], g["out"]) < 1e-5
     assert relerr(res["last_state"], g["last_state"]) < 1e-5
-    assert torch.allclose(res["out"].cpu(), torch.tensor(g["out"]), rtol=6e-4, atol=2e-3)
+    assert torch.allclose(res["out"].detach().cpu(), torch.tensor(g["out"]), rtol=6e-4, atol=2e-3)
     if not has_grads:
         return
     for k in ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz"):
@@ -104,9 +104,10 @@ def test_oracle_fp32(shape):
     for k in ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias"):
         assert relerr(res[k], gr64[k]) < 2e-5, k
     # the reference's own element-wise bounds
-    assert np.allclose(res["out"].cpu().numpy(), out64, rtol=6e-4, atol=2e-3)
-    assert np.allclose(res["du"].cpu().numpy(), gr64["du"], rtol=12e-4, atol=4e-3)
-    assert np.allclose(res["ddelta"].cpu().numpy(), gr64["ddelta"], rtol=30e-4, atol=2e-2)
+    npy = lambda k: res[k].detach().cpu().numpy()
+    assert np.allclose(npy("out"), out64, rtol=6e-4, atol=2e-3)
+    assert np.allclose(npy("du"), gr64["du"], rtol=12e-4, atol=4e-3)
+    assert np.allclose(npy("ddelta"), gr64["ddelta"], rtol=30e-4, atol=2e-2)
 
 
 def test_z_gate_matches_oracle():
@@ -133,7 +134,7 @@ def test_low_precision_io(dtype):
     res = run_cuda(g, dtype=dtype)
     assert res["out"].dtype == dtype and res["du"].dtype == dtype and res["dB"].dtype == dtype
     rtol, atol = (3e-2, 5e-2) if dtype == torch.bfloat16 else (3e-3, 5e-3)
-    f = lambda k: res[k].float().cpu().numpy()
+    f = lambda k: res[k].detach().float().cpu().numpy()
     assert np.allclose(f("out"), out64, rtol=rtol, atol=atol)
     assert np.allclose(f("du"), gr64["du"], rtol=2 * rtol, atol=2 * atol)
     assert np.allclose(f("ddelta"), gr64["ddelta"], rtol=5 * rtol, atol=10 * atol)
