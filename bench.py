@@ -258,6 +258,8 @@ def run_cuda(args):
     ddp = world > 1
     if ddp:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if not args.no_graph:  # NCCL collectives are captured into the step graph
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group(backend="nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234 + rank)
@@ -272,24 +274,31 @@ def run_cuda(args):
                     "host_cores": os.cpu_count()}
 
     net = medmamba_t(num_classes=NUM_CLASSES).to(dev)
+    use_graph = not args.no_graph
+    side = torch.cuda.Stream(device=dev)
     if ddp:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+        with torch.cuda.stream(side):  # DDP built on the capture-warm-up stream (PyTorch CUDA-graph + DDP recipe)
+            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+        torch.cuda.current_stream().wait_stream(side)
     else:
         model = net
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
     B = args.batch
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, NUM_CLASSES, (B,), device=dev)
     x_host = torch.randn(B, 3, 224, 224).pin_memory()
     y_host = torch.randint(0, NUM_CLASSES, (B,)).pin_memory()
 
-    def step(x, y):
-        opt.zero_grad(set_to_none=True)
+    def fwd_bwd_opt(x, y):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = torch.nn.functional.cross_entropy(model(x).float(), y)
         loss.backward()
         opt.step()
         return loss
+
+    def eager_step(x, y):
+        opt.zero_grad(set_to_none=True)
+        return fwd_bwd_opt(x, y)
 
     def barrier():
         if ddp:
@@ -298,24 +307,56 @@ def run_cuda(args):
 
     prof = ScanProfiler()
     prof.install()
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev)
+    # warm-up (also the >= 11 side-stream iterations DDP wants before a capture)
+    n_warm = max(args.warmup, 3, 11 if (use_graph and ddp) else 0)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(n_warm):
+            eager_step(x_dev, y_dev)
+    torch.cuda.current_stream().wait_stream(side)
+    barrier()
+
+    # ---- capture the whole step (forward, loss, backward, Adam) in one CUDA graph ----
+    graph, static_x, static_y, static_loss, graph_note = None, None, None, None, "eager"
+    if use_graph:
+        try:
+            static_x, static_y = x_dev.clone(), y_dev.clone()
+            opt.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = fwd_bwd_opt(static_x, static_y)
+            graph_note = "whole step captured in one CUDA graph"
+        except Exception as exc:  # keep measuring: fall back to eager launches and say so
+            graph, graph_note = None, f"eager (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
+            torch.cuda.synchronize(dev)
+            opt.zero_grad(set_to_none=True)
+
+    def run_step(x, y):
+        if graph is None:
+            return eager_step(x, y)
+        if x is not static_x:
+            static_x.copy_(x, non_blocking=True)
+            static_y.copy_(y, non_blocking=True)
+        graph.replay()
+        return static_loss
+
+    for _ in range(3):
+        run_step(static_x if graph is not None else x_dev, static_y if graph is not None else y_dev)
     barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    xin, yin = (static_x, static_y) if graph is not None else (x_dev, y_dev)
     # ---- timed region 1: inputs resident in HBM ----
-    prof.enabled = True
     launches0 = _lib.launches()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step(x_dev, y_dev)
+        run_step(xin, yin)
     e1.record()
     barrier()
     launches = _lib.launches() - launches0
-    prof.enabled = False
     ms = e0.elapsed_time(e1)
     # ---- timed region 2: end to end (pinned host input -> device, loss -> host) ----
     barrier()
@@ -323,13 +364,38 @@ def run_cuda(args):
     f0.record()
     last = 0.0
     for _ in range(args.steps):
-        xb = x_host.to(dev, non_blocking=True)
-        yb = y_host.to(dev, non_blocking=True)
-        last = step(xb, yb).item()
+        if graph is None:
+            xb = x_host.to(dev, non_blocking=True)
+            yb = y_host.to(dev, non_blocking=True)
+            last = eager_step(xb, yb).item()
+        else:
+            last = run_step(x_host, y_host).item()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     clocks = sampler.stop()
+    # ---- per-launch CUDA-event timing of the scan kernels: the same K steps, launched eagerly so the
+    #      events bracket each kernel on its stream (events cannot be read back from a graph replay) ----
+    kernel_launches_per_step = None
+    opt_e = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True) if graph is not None else opt
+
+    def eager_probe(x, y):
+        opt_e.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(model(x).float(), y)
+        loss.backward()
+        return loss
+
+    barrier()
+    l0 = _lib.launches()
+    prof.enabled = True
+    for _ in range(args.steps):
+        eager_probe(x_dev, y_dev)
+    prof.enabled = False
+    barrier()
+    kernel_launches_per_step = (_lib.launches() - l0) // args.steps
+    if graph is not None:
+        launches = kernel_launches_per_step * args.steps  # replays launch the captured kernels; count them from the eager twin
 
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if ddp:
@@ -344,7 +410,7 @@ def run_cuda(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
-                           "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-4 (fused)",
+                           "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-4 (fused)", "launch": graph_note,
                            "scan_io": "fp32 (as the reference calls it), fp32 state",
                            "l2": "per-step activations (> 10 GB) exceed the 126 MB L2; no explicit flush"},
                 "e2e": {"value": round(total / (ms_e2e / 1e3), 2), "unit": UNIT,
@@ -367,6 +433,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 64)")
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -389,7 +389,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     constexpr int TP = BwdSmem<TC, HAS_Z>::TP;
     constexpr int SP = BwdSmem<TC, HAS_Z>::SP;
     constexpr int NTHR = NW * 32;
-    constexpr int EP = (32 * TC + NTHR - 1) / NTHR;  // passes of the element-wise epilogue
+    constexpr int EP = (32 * (TC / 4) + NTHR - 1) / NTHR;  // passes of the (4 steps per thread) epilogue
     const int tid = threadIdx.x;
     const int lane = tid & 31, w = tid >> 5;
     const int L = p.seqlen, N = p.dstate;
@@ -411,7 +411,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
         sm.bias[tid] = (p.delta_bias && row_ok) ? __ldg(p.delta_bias + d_lane) : 0.f;
     }
     const bool softplus = p.delta_softplus != 0;
-    float dD_acc[EP], dbias_acc[EP];  // per-row sums, meaningful in the lanes mapped to column 0
+    float dD_acc[EP], dbias_acc[EP];  // this thread's share of the per-row sums (its rows are fixed across chunks)
 #pragma unroll
     for (int k = 0; k < EP; ++k) { dD_acc[k] = 0.f; dbias_acc[k] = 0.f; }
 
@@ -432,6 +432,8 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     const bool vec_d = can_vectorize<T>(p.delta, p.delta_row_stride, p.delta_batch_stride, 0, L);
     const bool vec_g = can_vectorize<T>(q.dout, q.dout_row_stride, q.dout_batch_stride, q.dout_group_stride, L);
     const bool vec_z = HAS_Z && can_vectorize<T>(p.z, p.z_row_stride, p.z_batch_stride, 0, L);
+    const bool vec_out = !HAS_Z && can_vectorize<T>(q.du, q.du_row_stride, q.du_batch_stride, 0, L) &&
+                         can_vectorize<T>(q.ddelta, q.ddelta_row_stride, q.ddelta_batch_stride, 0, L);
 
     const int nck = (L + TC - 1) / TC;
     const float* ck = p.ckpt + (size_t)blockIdx.x * (size_t)(nck - 1) * NS * 32;
@@ -606,38 +608,63 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
         }
         __syncthreads();  // (3)
 
-        // ---- per-element gradients: TC consecutive lanes share a row ----
+        // ---- per-element gradients, four steps per thread ----
 #pragma unroll
         for (int k = 0; k < EP; ++k) {
             const int idx = tid + k * NTHR;
-            if ((32 * TC) % NTHR != 0 && idx >= 32 * TC) break;
-            const int rr = idx / TC, cc = idx % TC;
-            const int l = l_lo + cc;
-            const bool ok = rr < t.nrows && l >= 0 && l < L;
-            float v1 = 0.f, v2 = 0.f, vy = 0.f;
+            if (idx < 32 * (TC / 4)) {
+                const int rr = idx / (TC / 4), cq = (idx % (TC / 4)) * 4;
+                float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, vy = v1;
 #pragma unroll
-            for (int ww = 0; ww < NW; ++ww) {
-                v1 += sm.part[ww][rr * SP + cc];
-                v2 += sm.part[ww][rr * SP + TC + cc];
-                if (HAS_Z) vy += sm.part[ww][rr * SP + 2 * TC + cc];
-            }
-            const float dlv = sm.d[buf][rr * TP + cc], uv = sm.u[buf][rr * TP + cc], gv = sm.g[buf][rr * TP + cc];
-            const float Dv = sm.D[rr];
-            const float du = fmaf(dlv, v1, Dv * gv);
-            float dd = fmaf(uv, v1, v2) * sm.sg[rr * TP + cc];  // chain rule through softplus (sg = 1 without it, 0 off-range)
-            if (!ok) dd = 0.f;
-            float sb = dd, sd = gv * uv;
+                for (int ww = 0; ww < NW; ++ww) {
+                    const float4 a1 = *reinterpret_cast<const float4*>(&sm.part[ww][rr * SP + cq]);
+                    const float4 a2 = *reinterpret_cast<const float4*>(&sm.part[ww][rr * SP + TC + cq]);
+                    v1.x += a1.x; v1.y += a1.y; v1.z += a1.z; v1.w += a1.w;
+                    v2.x += a2.x; v2.y += a2.y; v2.z += a2.z; v2.w += a2.w;
+                    if (HAS_Z) {
+                        const float4 a3 = *reinterpret_cast<const float4*>(&sm.part[ww][rr * SP + 2 * TC + cq]);
+                        vy.x += a3.x; vy.y += a3.y; vy.z += a3.z; vy.w += a3.w;
+                    }
+                }
+                const float4 d4 = *reinterpret_cast<const float4*>(&sm.d[buf][rr * TP + cq]);
+                const float4 u4 = *reinterpret_cast<const float4*>(&sm.u[buf][rr * TP + cq]);
+                const float4 g4 = *reinterpret_cast<const float4*>(&sm.g[buf][rr * TP + cq]);
+                const float4 s4 = *reinterpret_cast<const float4*>(&sm.sg[rr * TP + cq]);
+                const float Dv = sm.D[rr];
+                const float s1v[4] = {v1.x, v1.y, v1.z, v1.w}, s2v[4] = {v2.x, v2.y, v2.z, v2.w};
+                const float dlv[4] = {d4.x, d4.y, d4.z, d4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+                const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, sgv[4] = {s4.x, s4.y, s4.z, s4.w};
+                float du[4], dd[4];
 #pragma unroll
-            for (int m = TC / 2; m >= 1; m >>= 1) {
-                sb += __shfl_xor_sync(0xffffffffu, sb, m);
-                sd += __shfl_xor_sync(0xffffffffu, sd, m);
-            }
-            dbias_acc[k] += sb;
-            dD_acc[k] += sd;
-            if (ok) {
-                stg_stream(du_base + (size_t)rr * q.du_row_stride + l, du);
-                stg_stream(dd_base + (size_t)rr * q.ddelta_row_stride + l, dd);
-                if (HAS_Z) stg_stream(dz_base + (size_t)rr * q.dz_row_stride + l, sm.z[buf][rr * TP + cc] * fmaf(Dv, uv, vy));
+                for (int e = 0; e < 4; ++e) {
+                    du[e] = fmaf(dlv[e], s1v[e], Dv * gv[e]);
+                    // chain rule through softplus: sg = sigmoid(delta + bias) (1 without softplus, 0 off-range)
+                    dd[e] = fmaf(uv[e], s1v[e], s2v[e]) * sgv[e];
+                    dbias_acc[k] += dd[e];                  // off-range / padded rows contribute exact zeros
+                    dD_acc[k] = fmaf(gv[e], uv[e], dD_acc[k]);
+                }
+                if (rr < t.nrows) {
+                    const int l = l_lo + cq;
+                    if (vec_out) {
+                        if (l >= 0 && l < L) {
+                            __stcs(reinterpret_cast<float4*>((float*)du_base + (size_t)rr * q.du_row_stride + l),
+                                   make_float4(du[0], du[1], du[2], du[3]));
+                            __stcs(reinterpret_cast<float4*>((float*)dd_base + (size_t)rr * q.ddelta_row_stride + l),
+                                   make_float4(dd[0], dd[1], dd[2], dd[3]));
+                        }
+                    } else {
+                        const float4 z4 = HAS_Z ? *reinterpret_cast<const float4*>(&sm.z[buf][rr * TP + cq]) : make_float4(0, 0, 0, 0);
+                        const float dzc[4] = {z4.x, z4.y, z4.z, z4.w}, yv[4] = {vy.x, vy.y, vy.z, vy.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (l + e >= 0 && l + e < L) {
+                                stg_stream(du_base + (size_t)rr * q.du_row_stride + l + e, du[e]);
+                                stg_stream(dd_base + (size_t)rr * q.ddelta_row_stride + l + e, dd[e]);
+                                if (HAS_Z) stg_stream(dz_base + (size_t)rr * q.dz_row_stride + l + e, dzc[e] * fmaf(Dv, uv[e], yv[e]));
+                            }
+                        }
+                    }
+                }
             }
         }
         __syncthreads();  // (4) every thread is done with the raw tiles of this chunk
@@ -651,15 +678,21 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
         for (int j = 0; j < SPW; ++j)
             if (w * SPW + j < N) atomicAdd(q.dA + (size_t)d_lane * N + w * SPW + j, dAs[j]);
     }
-    // per-row sums live in the threads mapped to column 0 of each epilogue pass
+    // per-row sums: TC/4 consecutive threads share a row in every epilogue pass
 #pragma unroll
     for (int k = 0; k < EP; ++k) {
         const int idx = tid + k * NTHR;
-        if (idx < 32 * TC && (idx % TC) == 0) {
-            const int rr = idx / TC;
+        float sb = dbias_acc[k], sd = dD_acc[k];
+#pragma unroll
+        for (int m = TC / 8; m >= 1; m >>= 1) {
+            sb += __shfl_xor_sync(0xffffffffu, sb, m);
+            sd += __shfl_xor_sync(0xffffffffu, sd, m);
+        }
+        if (idx < 32 * (TC / 4) && (idx % (TC / 4)) == 0) {
+            const int rr = idx / (TC / 4);
             if (rr < t.nrows) {
-                if (q.ddelta_bias) atomicAdd(q.ddelta_bias + t.d0 + rr, dbias_acc[k]);
-                if (q.dD) atomicAdd(q.dD + t.d0 + rr, dD_acc[k]);
+                if (q.ddelta_bias) atomicAdd(q.ddelta_bias + t.d0 + rr, sb);
+                if (q.dD) atomicAdd(q.dD + t.d0 + rr, sd);
             }
         }
     }

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .cross import DIR_PERM, cross_scan_pack, scan_merge
+from .cross import cross_scan_pack, scan_merge
 from .selective_scan_interface import selective_scan_fn
 
 
@@ -72,15 +72,21 @@ class SS2D(nn.Module):
         self.forward_core = self.forward_core_fused
 
     # ---- the hot path --------------------------------------------------------------------------
+    @staticmethod
+    def _to_internal(w):
+        """Re-order a per-direction tensor (4, ...) from the reference order k = layout + 2*reverse
+        to the internal order 2*layout + reverse (cross.DIR_PERM) without an index tensor, so the
+        step stays CUDA-graph capturable."""
+        return w.view(2, 2, *w.shape[1:]).transpose(0, 1).reshape(w.shape)
+
     def _dir_params(self):
-        """Per-direction parameters re-ordered to the internal direction order (cross.DIR_PERM)."""
+        """Per-direction parameters in the internal direction order."""
         K, D, N = 4, self.d_inner, self.d_state
-        perm = list(DIR_PERM)
-        Wx = self.x_proj_weight.float()[perm]                       # (4, R+2N, D)
-        Wdt = self.dt_projs_weight.float()[perm]                    # (4, D, R)
-        bias = self.dt_projs_bias.float()[perm].reshape(-1)         # (4D)
-        As = -torch.exp(self.A_logs.float()).view(K, D, N)[perm].reshape(K * D, N)
-        Ds = self.Ds.float().view(K, D)[perm].reshape(-1)
+        Wx = self._to_internal(self.x_proj_weight.float())                         # (4, R+2N, D)
+        Wdt = self._to_internal(self.dt_projs_weight.float())                      # (4, D, R)
+        bias = self._to_internal(self.dt_projs_bias.float()).reshape(-1)           # (4D)
+        As = self._to_internal(-torch.exp(self.A_logs.float()).view(K, D, N)).reshape(K * D, N)
+        Ds = self._to_internal(self.Ds.float().view(K, D)).reshape(-1)
         return Wx, Wdt, bias, As, Ds
 
     def forward_core_fused(self, x: torch.Tensor):
