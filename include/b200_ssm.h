@@ -148,53 +148,60 @@ int b200_cross_merge_bwd(const void* dy, void* dys, int32_t batch, int32_t D, in
  *   S_t   = exp(dt'_t A[h]) S_{t-1} + dt'_t x_t (outer) B_t        S: (P, N) per (batch, head)
  *   y_t   = S_t C_t + D[h] x_t                                    (* silu(z_t) when z is given)
  *
- * x, z, out (batch, L, H, P); dt (batch, L, H); B, C (batch, L, G, N); A, D, dt_bias (H) f32.
+ * x, out (batch, L, H, P); dt (batch, L, H); B, C (batch, L, G, N); A, D, dt_bias (H) f32.
  * Every tensor is addressed by explicit element strides (the reference passes permuted views
- * whose L stride is 1).
+ * whose L stride is 1).  The gate z, D with a head dimension, seq_idx and
+ * cu_seqlens are never passed by the reference models (SSD/MedSSD.py:361-375) and are rejected
+ * by the host wrapper.  Evaluated chunk-wise (chunk_size steps): Y = (C B^T o decay) (dt X) +
+ * decay C S_prev, S_c = decay S_{c-1} + B^T (decay dt X); all contractions on tensor cores.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t batch, seqlen, nheads, headdim, n_groups, dstate, chunk_size;
-    int32_t io_dtype; /* x, dt, B, C, z, out */
+    int32_t io_dtype;   /* x, dt, B, C, out */
     int32_t dt_softplus;
-    int32_t D_has_hdim;
+    int32_t precision;  /* 0: fp32-accurate tensor-core products (3xTF32 split); 1: single-pass TF32
+                           (what the reference's Triton kernels do on fp32 inputs; exact for bf16 data) */
     float dt_min, dt_max;
     int64_t x_stride[4];   /* batch, L, head, p */
     int64_t dt_stride[3];  /* batch, L, head */
     int64_t B_stride[4];   /* batch, L, group, n */
     int64_t C_stride[4];
-    int64_t z_stride[4];
     int64_t out_stride[4];
     const void* x;
     const void* dt;
-    const float* A;
+    const float* A;        /* (H) */
     const void* B;
     const void* C;
-    const float* D;       /* (H) or (H, P), or NULL */
-    const void* z;        /* or NULL */
-    const float* dt_bias; /* or NULL */
+    const float* D;        /* (H) or NULL */
+    const float* dt_bias;  /* (H) or NULL */
     const float* initial_states; /* (batch, H, P, N) contiguous f32 or NULL */
-    void* out;
-    float* final_states;  /* (batch, H, P, N) contiguous f32 or NULL */
-    void* workspace;      /* b200_ssd_workspace_bytes() bytes: chunk states + decay tables kept for backward */
+    void* out;             /* (batch, L, H, P) io_dtype */
+    float* final_states;   /* (batch, H, P, N) contiguous f32 or NULL */
+    float* workspace;      /* b200_ssd_workspace_bytes() bytes, kept for the backward:
+                              dt' [b][h][c][Q] | cumsum(dt' A) [b][h][c][Q] | chunk-entry states
+                              [b][c][h][P][N] | C B^T [b][c][g][Q][Q] */
 } b200_ssd_fwd_params;
 
 typedef struct {
-    b200_ssd_fwd_params f;
+    b200_ssd_fwd_params f;  /* forward inputs + its workspace (f.out / f.final_states unused) */
     int64_t dout_stride[4];
     const void* dout;
-    /* all gradients are contiguous fp32 in the logical shapes of their primals */
+    /* gradients: contiguous fp32 in the logical shapes of their primals, written (not accumulated)
+       except the three reduced over batch/sequence, which the caller zero-fills */
     float* dx;       /* (batch, L, H, P) */
     float* ddt;      /* (batch, L, H) */
-    float* dB;       /* (batch, L, G, N)  (accumulated: caller zero-fills) */
-    float* dC;       /* (batch, L, G, N)  (accumulated: caller zero-fills) */
-    float* dA;       /* (H)   (accumulated: caller zero-fills) */
-    float* dD;       /* (H) or (H, P) or NULL (accumulated) */
-    float* ddt_bias; /* (H) or NULL (accumulated) */
-    float* dz;       /* (batch, L, H, P) or NULL */
+    float* dB;       /* (batch, L, G, N) */
+    float* dC;       /* (batch, L, G, N) */
+    float* dA;       /* (H)   accumulated */
+    float* dD;       /* (H) or NULL, accumulated */
+    float* ddt_bias; /* (H) or NULL, accumulated */
+    float* scratch;  /* b200_ssd_bwd_scratch_bytes() bytes */
 } b200_ssd_bwd_params;
 
 size_t b200_ssd_workspace_bytes(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim,
-                                int32_t dstate, int32_t chunk_size);
+                                int32_t n_groups, int32_t dstate, int32_t chunk_size);
+size_t b200_ssd_bwd_scratch_bytes(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim,
+                                  int32_t n_groups, int32_t dstate, int32_t chunk_size);
 int b200_ssd_fwd(const b200_ssd_fwd_params* p, b200_stream_t stream);
 int b200_ssd_bwd(const b200_ssd_bwd_params* p, b200_stream_t stream);
 

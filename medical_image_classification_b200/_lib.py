@@ -50,11 +50,11 @@ class SsdFwdParams(C.Structure):
     """b200_ssd_fwd_params."""
     _fields_ = [
         ("batch", i32), ("seqlen", i32), ("nheads", i32), ("headdim", i32), ("n_groups", i32), ("dstate", i32),
-        ("chunk_size", i32), ("io_dtype", i32), ("dt_softplus", i32), ("D_has_hdim", i32),
+        ("chunk_size", i32), ("io_dtype", i32), ("dt_softplus", i32), ("precision", i32),
         ("dt_min", f32), ("dt_max", f32),
         ("x_stride", i64 * 4), ("dt_stride", i64 * 3), ("B_stride", i64 * 4), ("C_stride", i64 * 4),
-        ("z_stride", i64 * 4), ("out_stride", i64 * 4),
-        ("x", vp), ("dt", vp), ("A", vp), ("B", vp), ("C", vp), ("D", vp), ("z", vp), ("dt_bias", vp),
+        ("out_stride", i64 * 4),
+        ("x", vp), ("dt", vp), ("A", vp), ("B", vp), ("C", vp), ("D", vp), ("dt_bias", vp),
         ("initial_states", vp), ("out", vp), ("final_states", vp), ("workspace", vp),
     ]
 
@@ -65,7 +65,7 @@ class SsdBwdParams(C.Structure):
         ("f", SsdFwdParams),
         ("dout_stride", i64 * 4),
         ("dout", vp), ("dx", vp), ("ddt", vp), ("dB", vp), ("dC", vp), ("dA", vp), ("dD", vp),
-        ("ddt_bias", vp), ("dz", vp),
+        ("ddt_bias", vp), ("scratch", vp),
     ]
 
 
@@ -75,7 +75,7 @@ _DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 EXPORTS = [
     "b200_sscan_ckpt_bytes", "b200_sscan_fwd", "b200_sscan_bwd",
     "b200_cross_scan_pack", "b200_cross_scan_pack_bwd", "b200_cross_merge", "b200_cross_merge_bwd",
-    "b200_ssd_workspace_bytes", "b200_ssd_fwd", "b200_ssd_bwd",
+    "b200_ssd_workspace_bytes", "b200_ssd_bwd_scratch_bytes", "b200_ssd_fwd", "b200_ssd_bwd",
     "b200_rmsnorm_gated_fwd", "b200_rmsnorm_gated_bwd",
     "b200_last_error", "b200_version", "b200_kernel_launches", "b200_sizeof_params",
 ]
@@ -103,7 +103,9 @@ def load() -> C.CDLL:
     lib.b200_sscan_ckpt_bytes.restype = C.c_size_t
     lib.b200_sscan_ckpt_bytes.argtypes = [i32] * 6
     lib.b200_ssd_workspace_bytes.restype = C.c_size_t
-    lib.b200_ssd_workspace_bytes.argtypes = [i32] * 6
+    lib.b200_ssd_workspace_bytes.argtypes = [i32] * 7
+    lib.b200_ssd_bwd_scratch_bytes.restype = C.c_size_t
+    lib.b200_ssd_bwd_scratch_bytes.argtypes = [i32] * 7
     lib.b200_sizeof_params.restype = C.c_size_t
     lib.b200_sizeof_params.argtypes = [i32]
     lib.b200_sscan_fwd.argtypes = [C.POINTER(SScanFwdParams), vp]
