@@ -44,6 +44,16 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+// exp(x) with a Cody-Waite split of log2(e): the error (~2 ulp of MUFU.EX2) does not grow with |x|,
+// unlike __expf (ex2(x * log2e): the rounding of the product costs |x| * 2^-24 relative).
+__device__ __forceinline__ float exp_acc(float x) {
+    const float xc = fminf(fmaxf(x, -87.f), 88.f);  // keeps 2^n a normal number; exp(-87) ~ 1.6e-38 is 0 in effect
+    const float n = rintf(xc * 1.4426950408889634f);
+    float f = fmaf(xc, 1.4426950216293335f, -n);
+    f = fmaf(xc, 1.9259629911266175e-8f, f);
+    return ex2(f) * __int_as_float(((int)n + 127) << 23);
+}
+
 // F.softplus(beta=1, threshold=20), selective_scan_interface.py:112-113 / fwd_kernel.cuh:153-156.
 __device__ __forceinline__ float softplus20(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 

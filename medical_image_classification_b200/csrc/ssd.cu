@@ -1,0 +1,997 @@
+// ssd.cu -- Mamba-2 SSD chunked scan (mamba_chunk_scan_combined), forward and backward, sm_100a.
+//
+// Replaces the un-vendored Triton kernels of mamba_ssm==2.2.2 that the reference calls at
+// SSD/MedSSD.py:361-375 (semantics: SURVEY.md section 8(a) row a7).  Chunk-wise evaluation with
+// chunk length Q (= chunk_size), per batch b, chunk c, head h (group g = h / (H/G)):
+//
+//   dt'_l  = clamp(softplus(dt_l + dt_bias_h))      cs_l = cumsum_{j<=l}(dt'_j A_h)   (within chunk)
+//   CB     = C B^T                                  (Q x Q, per group)
+//   Sloc   = sum_s exp(cs_Q - cs_s) dt'_s x_s (x) B_s            (P x N, per head)
+//   Sin[c+1] = exp(cs_Q) Sin[c] + Sloc[c]                          (state passing)
+//   y_l    = sum_{s<=l} CB[l,s] exp(cs_l - cs_s) dt'_s x_s + exp(cs_l) C_l Sin^T + D x_l
+//
+// Every contraction runs on the tensor cores through one CTA-level tile engine (TileMma below):
+// 128x64x32 tiles, operands staged global -> registers -> shared with the decay / dt' factors
+// applied on the way in, TF32 mma with the 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32 accumulate)
+// so that fp32 callers get fp32-accurate products (precision = 0), or a single TF32 pass
+// (precision = 1: what the reference's tl.dot does on fp32 inputs).  The dense C B^T and
+// state contractions additionally have a tcgen05 / TMEM path (ssd_tc.cu) selected by precision = 1.
+// The backward is the exact adjoint of the chunked forward; it re-uses the forward's dt', cs,
+// chunk-entry states and C B^T (workspace) and the forward output (for the "stable" d cs term).
+#include "common.cuh"
+
+namespace b200 {
+namespace ssd {
+
+constexpr int BM = 128, BN = 64, BK = 32;
+constexpr int NTHR = 256;
+constexpr int LDA_KM = BM + 8, LDA_MK = BK + 4;
+constexpr int LDB_KN = BN + 8, LDB_NK = BK + 4;
+constexpr int A_FLOATS = (BK * LDA_KM > BM * LDA_MK) ? BK * LDA_KM : BM * LDA_MK;  // 4608
+constexpr int B_FLOATS = (BK * LDB_KN > BN * LDB_NK) ? BK * LDB_KN : BN * LDB_NK;  // 2304
+constexpr int MAXQ = 256;
+
+struct Dims {
+    int batch, L, H, P, G, N, Q, nc, hpg;
+};
+
+struct Ws {  // views into the forward workspace
+    float* dtp;     // [b][h][nc][Q]
+    float* cs;      // [b][h][nc][Q]
+    float* states;  // [b][nc][h][P][N]
+    float* cb;      // [b][nc][g][Q][Q]
+};
+
+__host__ __device__ inline size_t ws_dt_floats(const Dims& d) { return (size_t)d.batch * d.H * d.nc * d.Q; }
+__host__ __device__ inline size_t ws_state_floats(const Dims& d) { return (size_t)d.batch * d.nc * d.H * d.P * d.N; }
+__host__ __device__ inline size_t ws_cb_floats(const Dims& d) { return (size_t)d.batch * d.nc * d.G * d.Q * d.Q; }
+
+static Dims make_dims(const b200_ssd_fwd_params& p) {
+    Dims d;
+    d.batch = p.batch; d.L = p.seqlen; d.H = p.nheads; d.P = p.headdim; d.G = p.n_groups; d.N = p.dstate; d.Q = p.chunk_size;
+    d.nc = (p.seqlen + p.chunk_size - 1) / p.chunk_size;
+    d.hpg = p.nheads / p.n_groups;
+    return d;
+}
+static Ws make_ws(float* base, const Dims& d) {
+    Ws w;
+    w.dtp = base;
+    w.cs = w.dtp + ws_dt_floats(d);
+    w.states = w.cs + ws_dt_floats(d);
+    w.cb = w.states + ws_state_floats(d);
+    return w;
+}
+
+// strided 4-D view (batch, L, head|group, inner)
+template <typename T>
+struct View4 {
+    const T* p;
+    int64_t s0, s1, s2, s3;
+    __device__ __forceinline__ float at(int b, int l, int h, int i) const {
+        return to_f32<T>(__ldg(p + b * s0 + l * s1 + h * s2 + i * s3));
+    }
+};
+template <typename T> static View4<T> view4(const void* p, const int64_t* s) { return View4<T>{(const T*)p, s[0], s[1], s[2], s[3]}; }
+
+// ---- tensor-core tile engine -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+struct Acc {
+    float v[2][4][4];  // [m16 block][n8 block][c0..c3] of this warp's 32x32 sub-tile
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[i][j][r] = 0.f;
+    }
+};
+
+// Fill one operand tile: logical [TI rows (m or n)][32 k].  KI = true: shared layout [k][i] (pitch TI+8),
+// best when the source is contiguous along i; KI = false: layout [i][k] (pitch 36), best when the
+// source is contiguous along k.  `i_fast` picks the thread -> element mapping so that global reads
+// coalesce along whichever of the two has stride 1 in memory.  f(i, k) returns the (already
+// transformed, bounds-checked) element.
+template <int TI, bool KI, class F>
+__device__ __forceinline__ void fill_tile(float* s, bool i_fast, F f) {
+    constexpr int LD = KI ? TI + 8 : BK + 4;
+    const int tid = threadIdx.x;
+    if (i_fast) {
+#pragma unroll
+        for (int it = 0; it < TI * BK / NTHR; ++it) {
+            const int idx = it * NTHR + tid;
+            const int i = idx % TI, k = idx / TI;
+            s[KI ? k * LD + i : i * LD + k] = f(i, k);
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < TI * BK / NTHR; ++it) {
+            const int idx = it * NTHR + tid;
+            const int k = idx % BK, i = idx / BK;
+            s[KI ? k * LD + i : i * LD + k] = f(i, k);
+        }
+    }
+}
+
+// acc += A_tile (128 x 32) * B_tile (64 x 32)^T for this warp's 32x32 sub-tile.
+template <bool A_KM, bool B_KN>
+__device__ __forceinline__ void warp_mma(Acc& acc, const float* As, const float* Bs, bool x3) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int m0 = (warp & 3) * 32, n0 = (warp >> 2) * 32;
+#pragma unroll
+    for (int ks = 0; ks < BK / 8; ++ks) {
+        const int k0 = ks * 8;
+        uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int m = m0 + mi * 16 + g + ((r & 1) ? 8 : 0);
+                const int k = k0 + t + ((r & 2) ? 4 : 0);
+                const float a = As[A_KM ? k * LDA_KM + m : m * LDA_MK + k];
+                ah[mi][r] = tf32_rna(a);
+                al[mi][r] = tf32_rna(a - __uint_as_float(ah[mi][r]));
+            }
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int n = n0 + ni * 8 + g;
+                const int k = k0 + t + (r ? 4 : 0);
+                const float b = Bs[B_KN ? k * LDB_KN + n : n * LDB_NK + k];
+                bh[ni][r] = tf32_rna(b);
+                bl[ni][r] = tf32_rna(b - __uint_as_float(bh[ni][r]));
+            }
+        }
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                if (x3) {  // small terms first
+                    mma_tf32(acc.v[mi][ni], al[mi], bh[ni]);
+                    mma_tf32(acc.v[mi][ni], ah[mi], bl[ni]);
+                }
+                mma_tf32(acc.v[mi][ni], ah[mi], bh[ni]);
+            }
+    }
+}
+
+// visit every accumulator element of this thread: fn(m, n, value&) with m in [0,128), n in [0,64)
+template <class F>
+__device__ __forceinline__ void for_each_acc(Acc& acc, F fn) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int m0 = (warp & 3) * 32, n0 = (warp >> 2) * 32;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) fn(m0 + mi * 16 + g + ((r & 2) ? 8 : 0), n0 + ni * 8 + 2 * t + (r & 1), acc.v[mi][ni][r]);
+}
+
+struct Smem {
+    float A[2][A_FLOATS];
+    float B[2][B_FLOATS];
+    float cs[2][MAXQ];
+    float dtp[2][MAXQ];
+    float red[8];
+};
+
+__device__ __forceinline__ Smem& smem_ref() {
+    extern __shared__ __align__(16) unsigned char raw[];
+    return *reinterpret_cast<Smem*>(raw);
+}
+
+// stage the (b, h, c) chunk's cs / dt' rows into shared memory buffer `hb`
+__device__ __forceinline__ void stage_cs(Smem& sm, int hb, const Ws& ws, const Dims& d, int b, int h, int c) {
+    const size_t off = (((size_t)b * d.H + h) * d.nc + c) * d.Q;
+    for (int i = threadIdx.x; i < d.Q; i += NTHR) {
+        sm.cs[hb][i] = ws.cs[off + i];
+        sm.dtp[hb][i] = ws.dtp[off + i];
+    }
+}
+
+__device__ __forceinline__ float block_sum(Smem& sm, float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NTHR / 32; ++w) s += sm.red[w];
+    return s;
+}
+
+// ---- K1: dt' = clamp(softplus(dt + bias)), cs = inclusive cumsum(dt' A) within each chunk -----
+template <typename T>
+__global__ void __launch_bounds__(MAXQ) dt_cumsum_kernel(const T* dt, int64_t s0, int64_t s1, int64_t s2, const float* A,
+                                                         const float* dt_bias, int softplus, float dt_min, float dt_max, Dims d,
+                                                         Ws ws) {
+    __shared__ float wsum[MAXQ / 32];
+    const int c = blockIdx.x % d.nc, h = (blockIdx.x / d.nc) % d.H, b = blockIdx.x / (d.nc * d.H);
+    const int i = threadIdx.x, l = c * d.Q + i;
+    float v = 0.f;
+    if (i < d.Q && l < d.L) {
+        v = to_f32<T>(__ldg(dt + b * s0 + l * s1 + h * s2)) + (dt_bias ? __ldg(dt_bias + h) : 0.f);
+        if (softplus) v = softplus20(v);
+        v = fminf(fmaxf(v, dt_min), dt_max);
+    }
+    float x = v * __ldg(A + h);
+    const int lane = i & 31, w = i >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    float pre = 0.f;
+    for (int j = 0; j < w; ++j) pre += wsum[j];
+    x += pre;
+    if (i < d.Q) {
+        const size_t off = (((size_t)b * d.H + h) * d.nc + c) * d.Q + i;
+        ws.dtp[off] = v;
+        ws.cs[off] = x;
+    }
+}
+
+// ---- K2 / B1: per (b, c, h):  out[p][n] = sum_s w_s src_x[s, p] src_b[s, n] -----------------------
+//   MODE 0 (chunk states):  src_x = x,    src_b = B,  w_s = exp(cs_Q - cs_s) dt'_s
+//   MODE 1 (d states):      src_x = dout, src_b = C,  w_s = exp(cs_s)
+// GEMM: M = n (128 per tile), N = p (64 per tile), K = s.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(NTHR, 2) chunk_state_kernel(View4<T> X, View4<T> Bv, Dims d, Ws ws, float* out, int x3) {
+    Smem& sm = smem_ref();
+    const int ntn = (d.N + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int tn = bid % ntn; bid /= ntn;
+    const int tp = bid % ntp; bid /= ntp;
+    const int h = bid % d.H; bid /= d.H;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int g = h / d.hpg;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int n0 = tn * BM, p0 = tp * BN;
+    stage_cs(sm, 0, ws, d, b, h, c);
+    __syncthreads();
+    const float csQ = sm.cs[0][d.Q - 1];
+    const bool a_ifast = Bv.s3 < Bv.s1, b_ifast = X.s3 < X.s1;
+    Acc acc;
+    acc.zero();
+    int buf = 0;
+    for (int k0 = 0; k0 < q; k0 += BK, buf ^= 1) {
+        fill_tile<BM, false>(sm.A[buf], a_ifast, [&](int i, int k) {
+            const int n = n0 + i, s = k0 + k;
+            return (n < d.N && s < q) ? Bv.at(b, l0 + s, g, n) : 0.f;
+        });
+        fill_tile<BN, false>(sm.B[buf], b_ifast, [&](int i, int k) {
+            const int p = p0 + i, s = k0 + k;
+            if (p >= d.P || s >= q) return 0.f;
+            const float w = MODE == 0 ? exp_acc(csQ - sm.cs[0][s]) * sm.dtp[0][s] : exp_acc(sm.cs[0][s]);
+            return X.at(b, l0 + s, h, p) * w;
+        });
+        __syncthreads();
+        warp_mma<false, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+    }
+    float* o = out + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
+    for_each_acc(acc, [&](int m, int n, float& v) {
+        const int nn = n0 + m, p = p0 + n;
+        if (nn < d.N && p < d.P) o[(size_t)p * d.N + nn] = v;
+    });
+}
+
+// ---- K3: state passing over chunks (in place: local states -> chunk-entry states) --------------
+__global__ void state_pass_kernel(Dims d, Ws ws, const float* init, float* fin) {
+    const size_t PN = (size_t)d.P * d.N;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)d.batch * d.H * PN) return;
+    const size_t e = idx % PN;
+    const int h = (idx / PN) % d.H, b = idx / (PN * d.H);
+    float run = init ? init[idx] : 0.f;
+    for (int c = 0; c < d.nc; ++c) {
+        float* s = ws.states + (((size_t)b * d.nc + c) * d.H + h) * PN + e;
+        const float loc = *s;
+        *s = run;
+        const float csQ = ws.cs[(((size_t)b * d.H + h) * d.nc + c) * d.Q + d.Q - 1];
+        run = exp_acc(csQ) * run + loc;
+    }
+    if (fin) fin[idx] = run;
+}
+
+// ---- K4: CB[l][s] = sum_n C[l, n] B[s, n]  per (b, c, g); only tiles touching s <= l ------------
+template <typename T>
+__global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, Dims d, Ws ws, int x3) {
+    Smem& sm = smem_ref();
+    const int ntm = (d.Q + BM - 1) / BM, ntn = (d.Q + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int tn = bid % ntn; bid /= ntn;
+    const int tm = bid % ntm; bid /= ntm;
+    const int g = bid % d.G; bid /= d.G;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int m0 = tm * BM, s0 = tn * BN;
+    if (m0 >= q || s0 >= q || s0 > m0 + BM - 1) return;
+    const bool a_ifast = Cv.s1 <= Cv.s3, b_ifast = Bv.s1 <= Bv.s3;
+    Acc acc;
+    acc.zero();
+    int buf = 0;
+    for (int k0 = 0; k0 < d.N; k0 += BK, buf ^= 1) {
+        fill_tile<BM, true>(sm.A[buf], a_ifast, [&](int i, int k) {
+            const int l = m0 + i, n = k0 + k;
+            return (l < q && n < d.N) ? Cv.at(b, l0 + l, g, n) : 0.f;
+        });
+        fill_tile<BN, true>(sm.B[buf], b_ifast, [&](int i, int k) {
+            const int s = s0 + i, n = k0 + k;
+            return (s < q && n < d.N) ? Bv.at(b, l0 + s, g, n) : 0.f;
+        });
+        __syncthreads();
+        warp_mma<true, true>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+    }
+    float* o = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
+    for_each_acc(acc, [&](int m, int n, float& v) {
+        const int l = m0 + m, s = s0 + n;
+        if (l < q && s < q) o[(size_t)l * d.Q + s] = v;
+    });
+}
+
+// ---- K5: y = (CB o decay) (dt' x) + exp(cs) C Sin^T + D x   per (b, c, h) ------------------------
+template <typename T>
+__global__ void __launch_bounds__(NTHR, 2) chunk_scan_kernel(View4<T> X, View4<T> Cv, const float* D, Dims d, Ws ws, T* out,
+                                                             int64_t o0, int64_t o1, int64_t o2, int64_t o3, int x3) {
+    Smem& sm = smem_ref();
+    const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int tp = bid % ntp; bid /= ntp;
+    const int tm = bid % ntm; bid /= ntm;
+    const int h = bid % d.H; bid /= d.H;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int g = h / d.hpg;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int m0 = tm * BM, p0 = tp * BN;
+    if (m0 >= q) return;
+    stage_cs(sm, 0, ws, d, b, h, c);
+    __syncthreads();
+    const float* cb = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
+    const float* Sin = ws.states + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
+    const bool x_ifast = X.s3 < X.s1, c_ifast = Cv.s1 <= Cv.s3;
+    Acc acc;
+    acc.zero();
+    int buf = 0;
+    // diagonal block: K runs over s <= l
+    const int send = min(q, m0 + BM);
+    for (int k0 = 0; k0 < send; k0 += BK, buf ^= 1) {
+        fill_tile<BM, false>(sm.A[buf], false, [&](int i, int k) {
+            const int l = m0 + i, s = k0 + k;
+            return (l < q && s <= l) ? cb[(size_t)l * d.Q + s] * exp_acc(sm.cs[0][l] - sm.cs[0][s]) : 0.f;
+        });
+        fill_tile<BN, false>(sm.B[buf], x_ifast, [&](int i, int k) {
+            const int p = p0 + i, s = k0 + k;
+            return (p < d.P && s < q) ? X.at(b, l0 + s, h, p) * sm.dtp[0][s] : 0.f;
+        });
+        __syncthreads();
+        warp_mma<false, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+    }
+    // off-diagonal block: contribution of the chunk-entry state
+    if (c > 0 || true) {
+        for (int k0 = 0; k0 < d.N; k0 += BK, buf ^= 1) {
+            fill_tile<BM, true>(sm.A[buf], c_ifast, [&](int i, int k) {
+                const int l = m0 + i, n = k0 + k;
+                return (l < q && n < d.N) ? Cv.at(b, l0 + l, g, n) * exp_acc(sm.cs[0][l]) : 0.f;
+            });
+            fill_tile<BN, false>(sm.B[buf], false, [&](int i, int k) {
+                const int p = p0 + i, n = k0 + k;
+                return (p < d.P && n < d.N) ? Sin[(size_t)p * d.N + n] : 0.f;
+            });
+            __syncthreads();
+            warp_mma<true, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+        }
+    }
+    const float Dh = D ? __ldg(D + h) : 0.f;
+    for_each_acc(acc, [&](int m, int n, float& v) {
+        const int l = m0 + m, p = p0 + n;
+        if (l < q && p < d.P) {
+            const float y = v + Dh * X.at(b, l0 + l, h, p);
+            out[b * o0 + (l0 + l) * o1 + h * o2 + p * o3] = from_f32<T>(y);
+        }
+    });
+}
+
+// ---- B2: reverse state passing: dstates[c] (off-diagonal adjoint) -> G[c] = adjoint of Sin[c+1];
+//          dcsQ[b][h][c] = <G[c], Sin[c+1]>  (accumulated with atomics; caller zero-fills) ----------
+__global__ void __launch_bounds__(NTHR) state_pass_bwd_kernel(Dims d, Ws ws, float* dstates, float* dcsQ) {
+    __shared__ float red[NTHR / 32];
+    const size_t PN = (size_t)d.P * d.N;
+    const int nblk = (int)((PN + NTHR - 1) / NTHR);
+    const int blk = blockIdx.x % nblk;
+    const int h = (blockIdx.x / nblk) % d.H, b = blockIdx.x / (nblk * d.H);
+    const size_t e = (size_t)blk * NTHR + threadIdx.x;
+    const bool ok = e < PN;
+    float run = 0.f;
+    for (int c = d.nc - 1; c >= 0; --c) {
+        float* s = dstates + (((size_t)b * d.nc + c) * d.H + h) * PN + e;
+        float off = 0.f;
+        if (ok) {
+            off = *s;
+            *s = run;
+        }
+        float dot = 0.f;
+        if (ok && c + 1 < d.nc) dot = run * ws.states[(((size_t)b * d.nc + c + 1) * d.H + h) * PN + e];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < NTHR / 32; ++w) t += red[w];
+            if (c + 1 < d.nc) atomicAdd(dcsQ + ((size_t)b * d.H + h) * d.nc + c, t);
+        }
+        __syncthreads();
+        const float csQ = ws.cs[(((size_t)b * d.H + h) * d.nc + c) * d.Q + d.Q - 1];
+        run = off + exp_acc(csQ) * run;
+    }
+}
+
+// ---- B3: Z = (CB o decay)^T dout + exp(cs_Q - cs) B G^T;  dx = dt' Z + D dout;
+//          ddtp_exp[s] = sum_p x Z;  dcs_pos[l] = sum_p dout (out - D x);  dD += sum dout x --------
+template <typename T>
+__global__ void __launch_bounds__(NTHR, 2) dx_kernel(View4<T> X, View4<T> Bv, View4<T> DO, View4<T> OUT, const float* D, Dims d, Ws ws,
+                                                     const float* G, float* dx, float* ddtp_exp, float* dcs_pos, float* dD, int x3) {
+    Smem& sm = smem_ref();
+    const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int tp = bid % ntp; bid /= ntp;
+    const int tm = bid % ntm; bid /= ntm;
+    const int h = bid % d.H; bid /= d.H;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int g = h / d.hpg;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int m0 = tm * BM, p0 = tp * BN;
+    if (m0 >= q) return;
+    stage_cs(sm, 0, ws, d, b, h, c);
+    __syncthreads();
+    const float csQ = sm.cs[0][d.Q - 1];
+    const float* cb = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
+    const float* Gs = G + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
+    const bool do_ifast = DO.s3 < DO.s1, b_ifast = Bv.s1 <= Bv.s3;
+    Acc acc;
+    acc.zero();
+    int buf = 0;
+    for (int k0 = (m0 / BK) * BK; k0 < q; k0 += BK, buf ^= 1) {  // l >= s
+        fill_tile<BM, true>(sm.A[buf], true, [&](int i, int k) {
+            const int s = m0 + i, l = k0 + k;
+            return (l < q && s <= l) ? cb[(size_t)l * d.Q + s] * exp_acc(sm.cs[0][l] - sm.cs[0][s]) : 0.f;
+        });
+        fill_tile<BN, false>(sm.B[buf], do_ifast, [&](int i, int k) {
+            const int p = p0 + i, l = k0 + k;
+            return (p < d.P && l < q) ? DO.at(b, l0 + l, h, p) : 0.f;
+        });
+        __syncthreads();
+        warp_mma<true, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+    }
+    if (c + 1 < d.nc) {  // G of the last chunk is identically zero
+        for (int k0 = 0; k0 < d.N; k0 += BK, buf ^= 1) {
+            fill_tile<BM, true>(sm.A[buf], b_ifast, [&](int i, int k) {
+                const int s = m0 + i, n = k0 + k;
+                return (s < q && n < d.N) ? Bv.at(b, l0 + s, g, n) * exp_acc(csQ - sm.cs[0][s]) : 0.f;
+            });
+            fill_tile<BN, false>(sm.B[buf], false, [&](int i, int k) {
+                const int p = p0 + i, n = k0 + k;
+                return (p < d.P && n < d.N) ? Gs[(size_t)p * d.N + n] : 0.f;
+            });
+            __syncthreads();
+            warp_mma<true, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+        }
+    }
+    const float Dh = D ? __ldg(D + h) : 0.f;
+    // epilogue: each thread owns rows (g, g+8) of two m16 blocks; accumulate its row sums per row slot
+    float r1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, r2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float dDl = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int s = m0 + wm0 + mi * 16 + gq + ((r & 2) ? 8 : 0), p = p0 + wn0 + ni * 8 + 2 * tq + (r & 1);
+                if (s < q && p < d.P) {
+                    const float z = acc.v[mi][ni][r];
+                    const float xv = X.at(b, l0 + s, h, p), dv = DO.at(b, l0 + s, h, p), ov = OUT.at(b, l0 + s, h, p);
+                    dx[(((size_t)b * d.L + l0 + s) * d.H + h) * d.P + p] = sm.dtp[0][s] * z + Dh * dv;
+                    r1[mi][r >> 1] += xv * z;
+                    r2[mi][r >> 1] += dv * (ov - Dh * xv);
+                    dDl += dv * xv;
+                }
+            }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            float a = r1[mi][hh], bb = r2[mi][hh];
+            a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+            bb += __shfl_xor_sync(0xffffffffu, bb, 1); bb += __shfl_xor_sync(0xffffffffu, bb, 2);
+            const int s = m0 + wm0 + mi * 16 + gq + hh * 8;
+            if (tq == 0 && s < q) {
+                const size_t off = (((size_t)b * d.H + h) * d.nc + c) * d.Q + s;
+                atomicAdd(ddtp_exp + off, a);
+                atomicAdd(dcs_pos + off, bb);
+            }
+        }
+    if (dD) {
+        const float tot = block_sum(sm, dDl);
+        if (threadIdx.x == 0) atomicAdd(dD + h, tot);
+    }
+}
+
+// ---- B4: dCB[l][s] = sum_{h in g} dt'_s exp(cs_l - cs_s) (dout_h x_h^T)[l, s],  s <= l ------------
+template <typename T>
+__global__ void __launch_bounds__(NTHR, 2) dcb_kernel(View4<T> X, View4<T> DO, Dims d, Ws ws, float* dcb, int x3) {
+    Smem& sm = smem_ref();
+    const int ntm = (d.Q + BM - 1) / BM, ntn = (d.Q + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int tn = bid % ntn; bid /= ntn;
+    const int tm = bid % ntm; bid /= ntm;
+    const int g = bid % d.G; bid /= d.G;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int m0 = tm * BM, s0 = tn * BN;
+    if (m0 >= q || s0 >= q || s0 > m0 + BM - 1) return;
+    const bool do_ifast = DO.s1 <= DO.s3, x_ifast = X.s1 <= X.s3;
+    Acc tot;
+    tot.zero();
+    int buf = 0;
+    for (int hh = 0; hh < d.hpg; ++hh) {
+        const int h = g * d.hpg + hh, hb = hh & 1;
+        stage_cs(sm, hb, ws, d, b, h, c);
+        __syncthreads();
+        Acc acc;
+        acc.zero();
+        for (int k0 = 0; k0 < d.P; k0 += BK, buf ^= 1) {
+            fill_tile<BM, true>(sm.A[buf], do_ifast, [&](int i, int k) {
+                const int l = m0 + i, p = k0 + k;
+                return (l < q && p < d.P) ? DO.at(b, l0 + l, h, p) : 0.f;
+            });
+            fill_tile<BN, true>(sm.B[buf], x_ifast, [&](int i, int k) {
+                const int s = s0 + i, p = k0 + k;
+                return (s < q && p < d.P) ? X.at(b, l0 + s, h, p) : 0.f;
+            });
+            __syncthreads();
+            warp_mma<true, true>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int gq = lane >> 2, tq = lane & 3;
+        const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int l = m0 + wm0 + mi * 16 + gq + ((r & 2) ? 8 : 0), s = s0 + wn0 + ni * 8 + 2 * tq + (r & 1);
+                    if (l < q && s <= l) tot.v[mi][ni][r] += sm.dtp[hb][s] * exp_acc(sm.cs[hb][l] - sm.cs[hb][s]) * acc.v[mi][ni][r];
+                }
+    }
+    float* o = dcb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
+    for_each_acc(tot, [&](int m, int n, float& v) {
+        const int l = m0 + m, s = s0 + n;
+        if (l < q && s < q) o[(size_t)l * d.Q + s] = v;
+    });
+}
+
+// ---- B5: dC = dCB B + sum_h exp(cs_h) dout_h Sin_h ;  dB = dCB^T C + sum_h exp(cs_Q - cs) dt' x_h G_h ----
+template <typename T>
+__global__ void __launch_bounds__(NTHR, 2) dbc_kernel(View4<T> X, View4<T> Bv, View4<T> Cv, View4<T> DO, Dims d, Ws ws,
+                                                      const float* dcb_all, const float* G, float* dB, float* dC, int x3) {
+    Smem& sm = smem_ref();
+    const int ntm = (d.Q + BM - 1) / BM, ntn = (d.N + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int which = bid & 1; bid >>= 1;  // 0: dC, 1: dB
+    const int tn = bid % ntn; bid /= ntn;
+    const int tm = bid % ntm; bid /= ntm;
+    const int g = bid % d.G; bid /= d.G;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int m0 = tm * BM, n0 = tn * BN;
+    if (m0 >= q) return;
+    const float* dcb = dcb_all + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
+    Acc acc;
+    acc.zero();
+    int buf = 0;
+    if (which == 0) {
+        const bool b_ifast = Bv.s3 < Bv.s1;
+        const int send = min(q, m0 + BM);
+        for (int k0 = 0; k0 < send; k0 += BK, buf ^= 1) {
+            fill_tile<BM, false>(sm.A[buf], false, [&](int i, int k) {
+                const int l = m0 + i, s = k0 + k;
+                return (l < q && s <= l) ? dcb[(size_t)l * d.Q + s] : 0.f;
+            });
+            fill_tile<BN, false>(sm.B[buf], b_ifast, [&](int i, int k) {
+                const int n = n0 + i, s = k0 + k;
+                return (n < d.N && s < q) ? Bv.at(b, l0 + s, g, n) : 0.f;
+            });
+            __syncthreads();
+            warp_mma<false, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+        }
+    } else {
+        const bool c_ifast = Cv.s3 < Cv.s1;
+        for (int k0 = (m0 / BK) * BK; k0 < q; k0 += BK, buf ^= 1) {
+            fill_tile<BM, true>(sm.A[buf], true, [&](int i, int k) {
+                const int s = m0 + i, l = k0 + k;
+                return (l < q && s <= l) ? dcb[(size_t)l * d.Q + s] : 0.f;
+            });
+            fill_tile<BN, false>(sm.B[buf], c_ifast, [&](int i, int k) {
+                const int n = n0 + i, l = k0 + k;
+                return (n < d.N && l < q) ? Cv.at(b, l0 + l, g, n) : 0.f;
+            });
+            __syncthreads();
+            warp_mma<true, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+        }
+    }
+    // state terms, head by head (K = p)
+    const View4<T>& Asrc = which == 0 ? DO : X;
+    const bool a_ifast = Asrc.s1 <= Asrc.s3;
+    const float* Sbase = which == 0 ? ws.states : G;
+    if (which == 0 || c + 1 < d.nc) {
+        for (int hh = 0; hh < d.hpg; ++hh) {
+            const int h = g * d.hpg + hh, hb = hh & 1;
+            stage_cs(sm, hb, ws, d, b, h, c);
+            __syncthreads();
+            const float csQ = sm.cs[hb][d.Q - 1];
+            const float* S = Sbase + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
+            for (int k0 = 0; k0 < d.P; k0 += BK, buf ^= 1) {
+                fill_tile<BM, true>(sm.A[buf], a_ifast, [&](int i, int k) {
+                    const int l = m0 + i, p = k0 + k;
+                    if (l >= q || p >= d.P) return 0.f;
+                    const float w = which == 0 ? exp_acc(sm.cs[hb][l]) : exp_acc(csQ - sm.cs[hb][l]) * sm.dtp[hb][l];
+                    return Asrc.at(b, l0 + l, h, p) * w;
+                });
+                fill_tile<BN, true>(sm.B[buf], true, [&](int i, int k) {
+                    const int n = n0 + i, p = k0 + k;
+                    return (n < d.N && p < d.P) ? S[(size_t)p * d.N + n] : 0.f;
+                });
+                __syncthreads();
+                warp_mma<true, true>(acc, sm.A[buf], sm.B[buf], x3 != 0);
+            }
+        }
+    }
+    float* o = which == 0 ? dC : dB;
+    for_each_acc(acc, [&](int m, int n, float& v) {
+        const int l = m0 + m, nn = n0 + n;
+        if (l < q && nn < d.N) o[(((size_t)b * d.L + l0 + l) * d.G + g) * d.N + nn] = v;
+    });
+}
+
+// ---- B6: d cs -> d(dt' A) (reverse cumsum) -> ddt', dA, ddt, ddt_bias ----------------------------
+template <typename T>
+__global__ void __launch_bounds__(MAXQ) dt_bwd_kernel(const T* dt, int64_t s0, int64_t s1, int64_t s2, const float* A,
+                                                      const float* dt_bias, int softplus, float dt_min, float dt_max, Dims d, Ws ws,
+                                                      const float* ddtp_exp, const float* dcs_pos, const float* dcsQ, float* ddt,
+                                                      float* dA, float* ddt_bias) {
+    __shared__ float wsum[MAXQ / 32];
+    __shared__ float red[2][MAXQ / 32];
+    const int c = blockIdx.x % d.nc, h = (blockIdx.x / d.nc) % d.H, b = blockIdx.x / (d.nc * d.H);
+    const int i = threadIdx.x, l = c * d.Q + i;
+    const size_t off = (((size_t)b * d.H + h) * d.nc + c) * d.Q + i;
+    const bool in = i < d.Q;
+    const float dtp = in ? ws.dtp[off] : 0.f;
+    const float de = in ? ddtp_exp[off] : 0.f;
+    float x = in ? dcs_pos[off] - dtp * de : 0.f;
+    if (i == d.Q - 1) x += dcsQ[((size_t)b * d.H + h) * d.nc + c];
+    // inclusive suffix sum over the chunk
+    const int lane = i & 31, w = i >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float y = __shfl_down_sync(0xffffffffu, x, o);
+        if (lane + o < 32) x += y;
+    }
+    if (lane == 0) wsum[w] = x;
+    __syncthreads();
+    float post = 0.f;
+    for (int j = w + 1; j < MAXQ / 32; ++j) post += (j * 32 < blockDim.x) ? wsum[j] : 0.f;
+    const float ddA = x + post;
+    const float Ah = __ldg(A + h);
+    const float ddtp = de + ddA * Ah;
+    float dAl = ddA * dtp, g = 0.f;
+    if (in && l < d.L) {
+        const float raw = to_f32<T>(__ldg(dt + b * s0 + l * s1 + h * s2)) + (dt_bias ? __ldg(dt_bias + h) : 0.f);
+        float v = raw, dv = 1.f;
+        if (softplus) {
+            v = softplus20(raw);
+            dv = raw > 20.f ? 1.f : 1.f / (1.f + expf(-raw));
+        }
+        if (v < dt_min || v > dt_max) dv = 0.f;
+        g = ddtp * dv;
+        ddt[((size_t)b * d.L + l) * d.H + h] = g;
+    } else {
+        dAl = 0.f;
+    }
+    float r0 = dAl, r1 = g;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+    }
+    if (lane == 0) { red[0][w] = r0; red[1][w] = r1; }
+    __syncthreads();
+    if (i == 0) {
+        float t0 = 0.f, t1 = 0.f;
+        for (int j = 0; j < (int)blockDim.x / 32; ++j) { t0 += red[0][j]; t1 += red[1][j]; }
+        atomicAdd(dA + h, t0);
+        if (ddt_bias) atomicAdd(ddt_bias + h, t1);
+    }
+}
+
+// ---- gated RMSNorm (SSD/MedSSD.py:393-394): y = rmsnorm(x silu(z)) w ------------------------------
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + expf(-z)); }
+
+__global__ void __launch_bounds__(256) rmsnorm_gated_fwd_kernel(const float* x, const float* z, const float* w, float* y, float* rstd,
+                                                                int64_t rows, int dim, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * dim;
+    const float* zr = z + row * dim;
+    float ss = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float v = xr[i] * silu_f(zr[i]);
+        ss += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float r = rsqrtf(ss / dim + eps);
+    if (lane == 0) rstd[row] = r;
+    float* yr = y + row * dim;
+    for (int i = lane; i < dim; i += 32) yr[i] = xr[i] * silu_f(zr[i]) * r * __ldg(w + i);
+}
+
+// dw_partial is (gridDim.x, dim): block-local sums over the block's rows (the host adds the rows up)
+__global__ void __launch_bounds__(256) rmsnorm_gated_bwd_kernel(const float* x, const float* z, const float* w, const float* rstd,
+                                                                const float* dy, float* dx, float* dz, float* dw_partial,
+                                                                int64_t rows, int dim, int rows_per_block) {
+    extern __shared__ float dw_s[];  // dim floats
+    for (int i = threadIdx.x; i < dim; i += 256) dw_s[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r_end = r_begin + rows_per_block < rows ? r_begin + rows_per_block : rows;
+    for (int64_t row = r_begin + warp; row < r_end; row += 8) {
+        const float* xr = x + row * dim;
+        const float* zr = z + row * dim;
+        const float* gr = dy + row * dim;
+        const float r = rstd[row];
+        float dot = 0.f;
+        for (int i = lane; i < dim; i += 32) {
+            const float vh = xr[i] * silu_f(zr[i]) * r;
+            dot += gr[i] * __ldg(w + i) * vh;
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        const float mean = dot / dim;
+        for (int i = lane; i < dim; i += 32) {
+            const float zz = zr[i], xx = xr[i];
+            const float sg = 1.f / (1.f + expf(-zz));
+            const float sl = zz * sg;
+            const float vh = xx * sl * r;
+            const float gy = gr[i];
+            const float dv = r * (gy * __ldg(w + i) - vh * mean);
+            dx[row * dim + i] = dv * sl;
+            dz[row * dim + i] = dv * xx * sg * (1.f + zz * (1.f - sg));
+            atomicAdd(&dw_s[i], gy * vh);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < dim; i += 256) dw_partial[(size_t)blockIdx.x * dim + i] = dw_s[i];
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+static int validate(const b200_ssd_fwd_params* p) {
+    B200_REQUIRE(p != nullptr, "b200_ssd: params is NULL");
+    B200_REQUIRE(p->batch > 0 && p->seqlen > 0 && p->nheads > 0 && p->headdim > 0 && p->dstate > 0,
+                 "b200_ssd: batch/seqlen/nheads/headdim/dstate must be positive (got %d/%d/%d/%d/%d)", p->batch, p->seqlen,
+                 p->nheads, p->headdim, p->dstate);
+    B200_REQUIRE(p->n_groups >= 1 && p->nheads % p->n_groups == 0, "b200_ssd: nheads %d is not divisible by n_groups %d", p->nheads,
+                 p->n_groups);
+    B200_REQUIRE(p->chunk_size >= 32 && p->chunk_size <= MAXQ && p->chunk_size % 32 == 0,
+                 "b200_ssd: chunk_size %d must be a multiple of 32 in [32, %d]", p->chunk_size, MAXQ);
+    B200_REQUIRE(p->io_dtype >= B200_F32 && p->io_dtype <= B200_F16, "b200_ssd: bad io_dtype %d", p->io_dtype);
+    B200_REQUIRE(p->x && p->dt && p->A && p->B && p->C, "b200_ssd: x/dt/A/B/C must be non-NULL");
+    B200_REQUIRE(p->workspace != nullptr, "b200_ssd: workspace is NULL");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 15) == 0, "b200_ssd: workspace must be 16-byte aligned");
+    return 0;
+}
+
+template <class K>
+static int set_smem(K kernel) {
+    static thread_local const void* done[32];
+    static thread_local int ndone = 0;
+    for (int i = 0; i < ndone; ++i)
+        if (done[i] == (const void*)kernel) return 0;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    if (ndone < 32) done[ndone++] = (const void*)kernel;
+    return 0;
+}
+
+#define LAUNCH(kernel, grid, block, smem, st, ...)                  \
+    do {                                                            \
+        if ((smem) > 0)                                             \
+            if (int rc_ = set_smem(kernel)) return rc_;             \
+        kernel<<<(unsigned)(grid), (block), (smem), (st)>>>(__VA_ARGS__); \
+        if (int rc_ = check_launch(#kernel)) return rc_;            \
+    } while (0)
+
+template <typename T>
+static int fwd_impl(const b200_ssd_fwd_params* p, cudaStream_t st) {
+    const Dims d = make_dims(*p);
+    const Ws ws = make_ws(p->workspace, d);
+    const View4<T> X = view4<T>(p->x, p->x_stride), Bv = view4<T>(p->B, p->B_stride), Cv = view4<T>(p->C, p->C_stride);
+    const int x3 = p->precision == 0;
+    const size_t SM = sizeof(Smem);
+    const int ntq128 = (d.Q + BM - 1) / BM, ntq64 = (d.Q + BN - 1) / BN;
+    const int ntn128 = (d.N + BM - 1) / BM, ntp64 = (d.P + BN - 1) / BN;
+    LAUNCH((dt_cumsum_kernel<T>), (size_t)d.batch * d.H * d.nc, d.Q, 0, st, (const T*)p->dt, p->dt_stride[0], p->dt_stride[1],
+           p->dt_stride[2], p->A, p->dt_bias, p->dt_softplus, p->dt_min, p->dt_max, d, ws);
+    LAUNCH((chunk_state_kernel<T, 0>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, X, Bv, d, ws, ws.states, x3);
+    {
+        const size_t n = (size_t)d.batch * d.H * d.P * d.N;
+        LAUNCH(state_pass_kernel, (n + 255) / 256, 256, 0, st, d, ws, p->initial_states, p->final_states);
+    }
+    LAUNCH((cb_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, Cv, Bv, d, ws, x3);
+    LAUNCH((chunk_scan_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Cv, p->D, d, ws, (T*)p->out,
+           p->out_stride[0], p->out_stride[1], p->out_stride[2], p->out_stride[3], x3);
+    return 0;
+}
+
+struct Scratch {
+    float* dstates;   // [b][nc][h][P][N]
+    float* dcb;       // [b][nc][g][Q][Q]
+    float* ddtp_exp;  // [b][h][nc][Q]
+    float* dcs_pos;   // [b][h][nc][Q]
+    float* dcsQ;      // [b][h][nc]
+};
+static size_t scratch_zero_floats(const Dims& d) { return 2 * ws_dt_floats(d) + (size_t)d.batch * d.H * d.nc; }
+static Scratch make_scratch(float* base, const Dims& d) {
+    Scratch s;
+    s.ddtp_exp = base;  // the three atomically-accumulated arrays first: one memset covers them
+    s.dcs_pos = s.ddtp_exp + ws_dt_floats(d);
+    s.dcsQ = s.dcs_pos + ws_dt_floats(d);
+    size_t off = scratch_zero_floats(d);
+    off = (off + 3) & ~(size_t)3;
+    s.dstates = base + off;
+    s.dcb = s.dstates + ws_state_floats(d);
+    return s;
+}
+
+template <typename T>
+static int bwd_impl(const b200_ssd_bwd_params* q, cudaStream_t st) {
+    const b200_ssd_fwd_params* p = &q->f;
+    const Dims d = make_dims(*p);
+    const Ws ws = make_ws(p->workspace, d);
+    const Scratch sc = make_scratch(q->scratch, d);
+    const View4<T> X = view4<T>(p->x, p->x_stride), Bv = view4<T>(p->B, p->B_stride), Cv = view4<T>(p->C, p->C_stride);
+    const View4<T> DO = view4<T>(q->dout, q->dout_stride), OUT = view4<T>(p->out, p->out_stride);
+    const int x3 = p->precision == 0;
+    const size_t SM = sizeof(Smem);
+    const int ntq128 = (d.Q + BM - 1) / BM, ntq64 = (d.Q + BN - 1) / BN;
+    const int ntn128 = (d.N + BM - 1) / BM, ntn64 = (d.N + BN - 1) / BN, ntp64 = (d.P + BN - 1) / BN;
+    const cudaError_t e = cudaMemsetAsync(sc.ddtp_exp, 0, scratch_zero_floats(d) * sizeof(float), st);
+    if (e != cudaSuccess) {
+        set_error("b200_ssd_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    LAUNCH((chunk_state_kernel<T, 1>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, DO, Cv, d, ws, sc.dstates, x3);
+    {
+        const int nblk = (int)(((size_t)d.P * d.N + NTHR - 1) / NTHR);
+        LAUNCH(state_pass_bwd_kernel, (size_t)d.batch * d.H * nblk, NTHR, 0, st, d, ws, sc.dstates, sc.dcsQ);
+    }
+    LAUNCH((dx_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Bv, DO, OUT, p->D, d, ws, sc.dstates, q->dx,
+           sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
+    LAUNCH((dcb_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, X, DO, d, ws, sc.dcb, x3);
+    LAUNCH((dbc_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntn64 * 2, NTHR, SM, st, X, Bv, Cv, DO, d, ws, sc.dcb, sc.dstates,
+           q->dB, q->dC, x3);
+    LAUNCH((dt_bwd_kernel<T>), (size_t)d.batch * d.H * d.nc, d.Q, 0, st, (const T*)p->dt, p->dt_stride[0], p->dt_stride[1],
+           p->dt_stride[2], p->A, p->dt_bias, p->dt_softplus, p->dt_min, p->dt_max, d, ws, sc.ddtp_exp, sc.dcs_pos, sc.dcsQ, q->ddt,
+           q->dA, q->ddt_bias);
+    return 0;
+}
+
+}  // namespace ssd
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::ssd;
+
+static bool dims_ok(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim, int32_t n_groups, int32_t dstate, int32_t chunk) {
+    return batch > 0 && seqlen > 0 && nheads > 0 && headdim > 0 && n_groups > 0 && dstate > 0 && chunk > 0 && nheads % n_groups == 0;
+}
+static Dims dims_of(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim, int32_t n_groups, int32_t dstate, int32_t chunk) {
+    Dims d;
+    d.batch = batch; d.L = seqlen; d.H = nheads; d.P = headdim; d.G = n_groups; d.N = dstate; d.Q = chunk;
+    d.nc = (seqlen + chunk - 1) / chunk;
+    d.hpg = nheads / n_groups;
+    return d;
+}
+
+extern "C" size_t b200_ssd_workspace_bytes(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim, int32_t n_groups,
+                                           int32_t dstate, int32_t chunk_size) {
+    if (!dims_ok(batch, seqlen, nheads, headdim, n_groups, dstate, chunk_size)) return 0;
+    const Dims d = dims_of(batch, seqlen, nheads, headdim, n_groups, dstate, chunk_size);
+    return (2 * ws_dt_floats(d) + ws_state_floats(d) + ws_cb_floats(d)) * sizeof(float);
+}
+
+extern "C" size_t b200_ssd_bwd_scratch_bytes(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim, int32_t n_groups,
+                                             int32_t dstate, int32_t chunk_size) {
+    if (!dims_ok(batch, seqlen, nheads, headdim, n_groups, dstate, chunk_size)) return 0;
+    const Dims d = dims_of(batch, seqlen, nheads, headdim, n_groups, dstate, chunk_size);
+    return (((scratch_zero_floats(d) + 3) & ~(size_t)3) + ws_state_floats(d) + ws_cb_floats(d)) * sizeof(float);
+}
+
+extern "C" int b200_ssd_fwd(const b200_ssd_fwd_params* p, b200_stream_t stream) {
+    if (int rc = ssd::validate(p)) return rc;
+    B200_REQUIRE(p->out != nullptr, "b200_ssd_fwd: out is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p->io_dtype) {
+        case B200_F32: return fwd_impl<float>(p, st);
+        case B200_BF16: return fwd_impl<__nv_bfloat16>(p, st);
+        default: return fwd_impl<__half>(p, st);
+    }
+}
+
+extern "C" int b200_ssd_bwd(const b200_ssd_bwd_params* q, b200_stream_t stream) {
+    B200_REQUIRE(q != nullptr, "b200_ssd_bwd: params is NULL");
+    if (int rc = ssd::validate(&q->f)) return rc;
+    B200_REQUIRE(q->f.out != nullptr, "b200_ssd_bwd: the forward output (f.out) is required");
+    B200_REQUIRE(q->dout && q->dx && q->ddt && q->dB && q->dC && q->dA && q->scratch,
+                 "b200_ssd_bwd: dout/dx/ddt/dB/dC/dA/scratch must be non-NULL");
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(q->scratch) & 15) == 0, "b200_ssd_bwd: scratch must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (q->f.io_dtype) {
+        case B200_F32: return bwd_impl<float>(q, st);
+        case B200_BF16: return bwd_impl<__nv_bfloat16>(q, st);
+        default: return bwd_impl<__half>(q, st);
+    }
+}
+
+extern "C" int b200_rmsnorm_gated_fwd(const float* x, const float* z, const float* w, float* y, float* rstd, int64_t rows, int32_t dim,
+                                      float eps, b200_stream_t stream) {
+    B200_REQUIRE(x && z && w && y && rstd, "b200_rmsnorm_gated_fwd: NULL pointer");
+    B200_REQUIRE(rows > 0 && dim > 0, "b200_rmsnorm_gated_fwd: rows/dim must be positive");
+    rmsnorm_gated_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, z, w, y, rstd, rows, dim, eps);
+    return check_launch("rmsnorm_gated_fwd_kernel");
+}
+
+extern "C" int b200_rmsnorm_gated_bwd(const float* x, const float* z, const float* w, const float* rstd, const float* dy, float* dx,
+                                      float* dz, float* dw_partial, int32_t dw_rows, int64_t rows, int32_t dim, b200_stream_t stream) {
+    B200_REQUIRE(x && z && w && rstd && dy && dx && dz && dw_partial, "b200_rmsnorm_gated_bwd: NULL pointer");
+    B200_REQUIRE(rows > 0 && dim > 0 && dw_rows > 0, "b200_rmsnorm_gated_bwd: rows/dim/dw_rows must be positive");
+    B200_REQUIRE(dim <= 12288, "b200_rmsnorm_gated_bwd: dim %d too large", dim);
+    const int rpb = (int)((rows + dw_rows - 1) / dw_rows);
+    rmsnorm_gated_bwd_kernel<<<(unsigned)dw_rows, 256, dim * sizeof(float), (cudaStream_t)stream>>>(x, z, w, rstd, dy, dx, dz, dw_partial,
+                                                                                                  rows, dim, rpb);
+    return check_launch("rmsnorm_gated_bwd_kernel");
+}

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .ss2d import SS2D
+from .ss2d_ssd import SS2D_with_SSD
 
 
 class DropPath(nn.Module):
@@ -99,14 +100,37 @@ class SS_Conv_SSM(nn.Module):
         return out + input
 
 
+class SS_Conv_SSD(SS_Conv_SSM):
+    """The same two-branch block with the SSD mixer (reference SSD/MedSSD.py:421-457)."""
+
+    def __init__(self, hidden_dim=0, drop_path=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6),
+                 attn_drop_rate=0.0, d_state=64, **kwargs):
+        nn.Module.__init__(self)
+        c = hidden_dim // 2
+        self.ln_1 = norm_layer(c)
+        self.self_attention = SS2D_with_SSD(d_model=c, dropout=attn_drop_rate, d_state=d_state, **kwargs)
+        self.drop_path = DropPath(drop_path)
+        self.conv33conv33conv11 = nn.Sequential(
+            nn.BatchNorm2d(c),
+            nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1),
+            nn.BatchNorm2d(c),
+            nn.ReLU(),
+            nn.Conv2d(c, c, kernel_size=3, stride=1, padding=1),
+            nn.BatchNorm2d(c),
+            nn.ReLU(),
+            nn.Conv2d(c, c, kernel_size=1, stride=1),
+            nn.ReLU(),
+        )
+
+
 class VSSLayer(nn.Module):
     def __init__(self, dim, depth, attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, downsample=None,
-                 use_checkpoint=False, d_state=16, **kwargs):
+                 use_checkpoint=False, d_state=16, block=SS_Conv_SSM, **kwargs):
         super().__init__()
         self.dim = dim
         self.use_checkpoint = use_checkpoint
         self.blocks = nn.ModuleList([
-            SS_Conv_SSM(hidden_dim=dim, drop_path=drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
+            block(hidden_dim=dim, drop_path=drop_path[i] if isinstance(drop_path, (list, tuple)) else drop_path,
                         norm_layer=norm_layer, attn_drop_rate=attn_drop, d_state=d_state)
             for i in range(depth)])
         self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
@@ -120,7 +144,7 @@ class VSSLayer(nn.Module):
 class VSSM(nn.Module):
     def __init__(self, patch_size=4, in_chans=3, num_classes=1000, depths=(2, 2, 4, 2), dims=(96, 192, 384, 768),
                  d_state=16, drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=nn.LayerNorm,
-                 patch_norm=True, use_checkpoint=False, **kwargs):
+                 patch_norm=True, use_checkpoint=False, block=SS_Conv_SSM, **kwargs):
         super().__init__()
         depths, n = list(depths), len(depths)
         dims = [int(dims * 2 ** i) for i in range(n)] if isinstance(dims, int) else list(dims)
@@ -135,7 +159,7 @@ class VSSM(nn.Module):
             self.layers.append(VSSLayer(
                 dim=dims[i], depth=depths[i], d_state=d_state, attn_drop=attn_drop_rate,
                 drop_path=dpr[sum(depths[:i]):sum(depths[:i + 1])], norm_layer=norm_layer,
-                downsample=PatchMerging2D if i < n - 1 else None, use_checkpoint=use_checkpoint))
+                downsample=PatchMerging2D if i < n - 1 else None, use_checkpoint=use_checkpoint, block=block))
         self.avgpool = nn.AdaptiveAvgPool2d(1)
         self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
         self.apply(self._init_weights)
@@ -168,3 +192,9 @@ class VSSM(nn.Module):
 def medmamba_t(num_classes=6, **kw):
     """MedMamba-T, the configuration BASELINE.json names (depths 2-2-4-2, dims 96-768)."""
     return VSSM(num_classes=num_classes, depths=[2, 2, 4, 2], dims=[96, 192, 384, 768], **kw)
+
+
+def medssd(num_classes=6, dims=(128, 256, 512, 1024), d_state=128, **kw):
+    """MedSSD: the SSD/MedSSD.py VSSM defaults (depths 2-2-4-2, dims 128-1024, d_state 128), BASELINE.json configs[2].
+    MedSSD_kan / CNN_Mamba backbones are the same graph with d_state=16."""
+    return VSSM(num_classes=num_classes, depths=[2, 2, 4, 2], dims=list(dims), d_state=d_state, block=SS_Conv_SSD, **kw)

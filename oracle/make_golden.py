@@ -15,6 +15,9 @@ It imports the UNMODIFIED reference Python (oracle/ref_import.py) and records, f
 * ss2d_*.npz    -- reference SS2D module (MedMamba.py:253-483) forward/backward with its state_dict.
 * vssm_tiny.npz -- reference VSSM (MedMamba.py:671-767) eval logits + train-mode grads, tiny dims.
 
+* ss2d_ssd_*.npz / medssd_tiny.npz -- reference SS2D_with_SSD / VSSM (SSD/MedSSD.py) with mamba_ssm's operator
+                   replaced by the oracle (module data flow pinned; operator itself PARITY UNPINNED).
+
 The vectors travel to the GPU box; the reference does not.
 """
 from __future__ import annotations
@@ -133,10 +136,66 @@ def vssm_case(seed=0):
     print("wrote vssm_tiny loss", float(loss))
 
 
+def ss2d_ssd_case(name, d_model, d_state, headdim, H, W, batch, seed=0):
+    """Reference SS2D_with_SSD (SSD/MedSSD.py:160-402) forward/backward with its state_dict; the SSD operator is the
+    oracle stand-in (ref_import.load_medssd), so this pins the module's data flow, not the operator."""
+    ms = ref_import.load_medssd()
+    torch.manual_seed(seed)
+    m = ms.SS2D_with_SSD(d_model=d_model, d_state=d_state, headdim=headdim, chunk_size=32)
+    with torch.no_grad():
+        m.Ds.add_(0.5 * torch.randn_like(m.Ds))
+        m.A_logs.add_(0.3 * torch.randn_like(m.A_logs))
+        m.dt_bias.add_(0.3 * torch.randn_like(m.dt_bias))
+        m.norm.weight.add_(0.2 * torch.randn_like(m.norm.weight))
+    x = torch.randn(batch, H, W, d_model, requires_grad=True)
+    g = torch.randn(batch, H, W, d_model)
+    out = m(x)
+    out.backward(g)
+    rec = {"x": _np(x), "g": _np(g), "out": _np(out), "dx": _np(x.grad),
+           "cfg": np.array([d_model, d_state, headdim, H, W, batch])}
+    for k, v in m.state_dict().items():
+        rec["sd." + k] = _np(v)
+    for k, p in m.named_parameters():
+        rec["grad." + k] = _np(p.grad)
+    np.savez_compressed(os.path.join(OUT, f"ss2d_ssd_{name}.npz"), **rec)
+    print("wrote ss2d_ssd", name, float(out.abs().max()))
+
+
+def medssd_case(seed=0):
+    ms = ref_import.load_medssd()
+    torch.manual_seed(seed)
+    kw = dict(num_classes=6, depths=[1, 1], dims=[64, 128], d_state=8, drop_path_rate=0.0)
+    net = ms.VSSM(**kw)
+    x = torch.randn(2, 3, 64, 64)
+    y = torch.randint(0, 6, (2,))
+    rec = {"x": _np(x), "y": _np(y)}
+    for k, v in net.state_dict().items():
+        rec["sd." + k] = _np(v)
+    net.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = _np(net(x))
+    net.train()
+    logits = net(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    rec["logits_train"] = _np(logits)
+    rec["loss"] = _np(loss)
+    for k, p in net.named_parameters():
+        if p.grad is not None and p.numel() <= 2048:
+            rec["grad." + k] = _np(p.grad)
+    np.savez_compressed(os.path.join(OUT, "medssd_tiny.npz"), **rec)
+    print("wrote medssd_tiny loss", float(loss))
+
+
 def main():
     assert ref_import.available(), "/root/reference is not mounted"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--ssd-only" in sys.argv:
+        ss2d_ssd_case("d32_7x5", 32, 8, 16, 7, 5, 2)
+        ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
+        medssd_case()
+        return
     # reference test-grid style (dstate=1, G in {1 (3-D B/C), 2})
     sscan_case("grid_g1", 2, 24, 1, 64, 1, True, True, True, bc_3d=True)
     sscan_case("grid_g2_plain", 2, 24, 1, 64, 2, False, False, False)
@@ -151,6 +210,9 @@ def main():
     ss2d_case("d8_7x5", 8, 7, 5, 2)
     ss2d_case("d16_4x6", 16, 4, 6, 1)
     vssm_case()
+    ss2d_ssd_case("d32_7x5", 32, 8, 16, 7, 5, 2)
+    ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
+    medssd_case()
 
 
 if __name__ == "__main__":

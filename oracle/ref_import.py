@@ -100,3 +100,87 @@ def load_medmamba(selective_scan_fn=None):
                 sys.modules[k] = v
     mod.selective_scan_fn = fn
     return mod
+
+
+def _oracle_ssd_fn():
+    """CPU stand-in for mamba_ssm's mamba_chunk_scan_combined: torch autograd over the from-definition oracle
+    (oracle/ssd_oracle.c).  mamba_ssm==2.2.2 is not vendored in the reference (PARITY UNPINNED for the operator);
+    what the golden vectors made with this stand-in DO pin is the reference module's data flow around the operator
+    (SSD/MedSSD.py:310-402: projections, conv, cross-scan, the one-group / 4*d_state quirk, cross-merge, gated norm)."""
+    import numpy as np
+    import torch
+    import oracle
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, dt, A, B, C, D, dt_bias, dt_softplus):
+            out, _ = oracle.ssd_fwd(x, dt, A, B, C, D=D, dt_bias=dt_bias, dt_softplus=dt_softplus)
+            ctx.save_for_backward(x, dt, A, B, C, D, dt_bias)
+            ctx.softplus = dt_softplus
+            return torch.from_numpy(out)
+
+        @staticmethod
+        def backward(ctx, dout):
+            x, dt, A, B, C, D, dt_bias = ctx.saved_tensors
+            g = oracle.ssd_bwd(x, dt, A, B, C, D=D, dt_bias=dt_bias, dt_softplus=ctx.softplus, dout=dout.contiguous())
+            t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a))
+            return t(g["dx"]), t(g["ddt"]), t(g["dA"]), t(g["dB"]), t(g["dC"]), t(g["dD"]), t(g["ddt_bias"]), None
+
+    def mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initial_states=None,
+                                  seq_idx=None, cu_seqlens=None, dt_softplus=False, dt_limit=(0.0, float("inf")),
+                                  return_final_states=False):
+        assert z is None and initial_states is None and seq_idx is None and cu_seqlens is None and not return_final_states
+        return Fn.apply(x, dt, A, B, C, D, dt_bias, dt_softplus)
+
+    return mamba_chunk_scan_combined
+
+
+def load_medssd():
+    """Reference SSD/MedSSD.py with mamba_ssm's pieces replaced by CPU stand-ins: the SSD operator by the oracle,
+    the gated RMSNorm by its published formula y = rmsnorm(x * silu(z)) * w (norm_before_gate=False)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    _timm_shim()
+
+    class RMSNorm(nn.Module):
+        def __init__(self, hidden_size, eps=1e-5, group_size=None, norm_before_gate=True, device=None, dtype=None):
+            super().__init__()
+            assert not norm_before_gate and (group_size is None or group_size == hidden_size)
+            self.eps = eps
+            self.weight = nn.Parameter(torch.ones(hidden_size, device=device, dtype=dtype))
+            self.register_parameter("bias", None)
+
+        def forward(self, x, z=None):
+            v = x * F.silu(z)
+            return v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps) * self.weight
+
+    names = ["mamba_ssm", "mamba_ssm.ops", "mamba_ssm.ops.triton", "mamba_ssm.ops.triton.layernorm_gated",
+             "mamba_ssm.ops.triton.ssd_combined", "mamba_ssm.ops.triton.selective_state_update",
+             "mamba_ssm.distributed", "mamba_ssm.distributed.tensor_parallel", "mamba_ssm.distributed.distributed_utils"]
+    mods = {n: types.ModuleType(n) for n in names}
+    mods["mamba_ssm.ops.triton.layernorm_gated"].RMSNorm = RMSNorm
+    mods["mamba_ssm.ops.triton.ssd_combined"].mamba_chunk_scan_combined = _oracle_ssd_fn()
+    mods["mamba_ssm.ops.triton.ssd_combined"].mamba_split_conv1d_scan_combined = None
+    mods["mamba_ssm.ops.triton.selective_state_update"].selective_state_update = None
+    mods["mamba_ssm.distributed.tensor_parallel"].ColumnParallelLinear = None
+    mods["mamba_ssm.distributed.tensor_parallel"].RowParallelLinear = None
+    mods["mamba_ssm.distributed.distributed_utils"].all_reduce = None
+    mods["mamba_ssm.distributed.distributed_utils"].reduce_scatter = None
+    saved = {k: sys.modules.get(k) for k in names}
+    sys.modules.update(mods)
+    try:
+        import huggingface_hub  # noqa: F401
+    except Exception:
+        hub = types.ModuleType("huggingface_hub")
+        hub.PyTorchModelHubMixin = type("PyTorchModelHubMixin", (), {})
+        sys.modules["huggingface_hub"] = hub
+    try:
+        mod = _load("ref_MedSSD", os.path.join(REF_ROOT, "SSD/MedSSD.py"))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
