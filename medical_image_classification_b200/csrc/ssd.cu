@@ -98,11 +98,91 @@ struct Acc {
     }
 };
 
-// Fill one operand tile: logical [TI rows (m or n)][32 k].  KI = true: shared layout [k][i] (pitch TI+8),
-// best when the source is contiguous along i; KI = false: layout [i][k] (pitch 36), best when the
-// source is contiguous along k.  `i_fast` picks the thread -> element mapping so that global reads
-// coalesce along whichever of the two has stride 1 in memory.  f(i, k) returns the (already
-// transformed, bounds-checked) element.
+// ---- operand tiles: global -> registers (raw, 128-bit when possible) -> shared (transformed) ----------
+// Logical tile [TI rows (m or n index i)][32 k].  KI = true: shared layout [k][i] (pitch TI+8) and the
+// register tile is vectorised along i (sources contiguous along i); KI = false: layout [i][k]
+// (pitch 36), vectorised along k.  Thread -> element mapping (vid = it*256 + tid):
+//   KI : i = 4 * (vid % (TI/4)), k = vid / (TI/4)          !KI : k = 4 * (vid % 8), i = vid / 8
+template <int TI>
+struct RegTile {
+    static constexpr int NV = TI * BK / 4 / NTHR;
+    float4 v[NV];
+};
+
+template <typename T> __device__ __forceinline__ float ld1(const T* p) { return to_f32<T>(__ldg(p)); }
+
+// p: element (i = 0, k = 0) of this k-tile; si / sk element strides; ni / nk valid extents (elements
+// outside read as 0); vec: T is float, the vector dimension has stride 1 and every vector is 16-byte aligned.
+template <int TI, bool KI, typename T>
+__device__ __forceinline__ void load_raw(RegTile<TI>& r, const T* p, int64_t si, int64_t sk, int ni, int nk, bool vec) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < RegTile<TI>::NV; ++it) {
+        const int vid = it * NTHR + tid;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (KI) {
+            const int i = (vid % (TI / 4)) * 4, k = vid / (TI / 4);
+            if (k < nk && i < ni) {
+                const T* q = p + (int64_t)i * si + (int64_t)k * sk;
+                if (sizeof(T) == 4 && vec && i + 3 < ni) {
+                    v = __ldg(reinterpret_cast<const float4*>(q));
+                } else {
+                    v.x = ld1(q);
+                    if (i + 1 < ni) v.y = ld1(q + si);
+                    if (i + 2 < ni) v.z = ld1(q + 2 * si);
+                    if (i + 3 < ni) v.w = ld1(q + 3 * si);
+                }
+            }
+        } else {
+            const int k = (vid % (BK / 4)) * 4, i = vid / (BK / 4);
+            if (i < ni && k < nk) {
+                const T* q = p + (int64_t)i * si + (int64_t)k * sk;
+                if (sizeof(T) == 4 && vec && k + 3 < nk) {
+                    v = __ldg(reinterpret_cast<const float4*>(q));
+                } else {
+                    v.x = ld1(q);
+                    if (k + 1 < nk) v.y = ld1(q + sk);
+                    if (k + 2 < nk) v.z = ld1(q + 2 * sk);
+                    if (k + 3 < nk) v.w = ld1(q + 3 * sk);
+                }
+            }
+        }
+        r.v[it] = v;
+    }
+}
+
+// xf(i, k, raw) -> the operand element (decay / dt' factors, causal mask); i, k local to the tile
+template <int TI, bool KI, class XF>
+__device__ __forceinline__ void store_tile(float* s, const RegTile<TI>& r, XF xf) {
+    constexpr int LD = KI ? TI + 8 : BK + 4;
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < RegTile<TI>::NV; ++it) {
+        const int vid = it * NTHR + tid;
+        const float4 v = r.v[it];
+        if (KI) {
+            const int i = (vid % (TI / 4)) * 4, k = vid / (TI / 4);
+            *reinterpret_cast<float4*>(s + k * LD + i) = make_float4(xf(i, k, v.x), xf(i + 1, k, v.y), xf(i + 2, k, v.z), xf(i + 3, k, v.w));
+        } else {
+            const int k = (vid % (BK / 4)) * 4, i = vid / (BK / 4);
+            *reinterpret_cast<float4*>(s + i * LD + k) = make_float4(xf(i, k, v.x), xf(i, k + 1, v.y), xf(i, k + 2, v.z), xf(i, k + 3, v.w));
+        }
+    }
+}
+
+struct Identity {
+    __device__ __forceinline__ float operator()(int, int, float v) const { return v; }
+};
+
+// can a [rows][cols] float source with these strides be read with aligned 128-bit loads along `vec_stride`'s dimension?
+template <typename T>
+__device__ __forceinline__ bool vec_ok(const T* p, int64_t vec_stride, int64_t other_stride) {
+    return sizeof(T) == 4 && vec_stride == 1 && (other_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+// Element-wise tile fill used by the backward kernels (not yet on the register-staged pipeline above):
+// same layouts; `i_fast` picks the thread -> element mapping so that global reads coalesce along whichever
+// of i / k has stride 1 in memory.  f(i, k) returns the (already transformed, bounds-checked) element.
 template <int TI, bool KI, class F>
 __device__ __forceinline__ void fill_tile(float* s, bool i_fast, F f) {
     constexpr int LD = KI ? TI + 8 : BK + 4;
@@ -188,8 +268,39 @@ struct Smem {
     float B[2][B_FLOATS];
     float cs[2][MAXQ];
     float dtp[2][MAXQ];
+    float v1[2][MAXQ];            // per-position factor vectors (kernel specific)
+    float v2[2][MAXQ];
+    float rowf[MAXQ / BK][BM];    // per (k-tile, row) decay factors of the diagonal-block contractions
     float red[8];
 };
+
+// One software-pipelined pass over nkt k-tiles: the raw tile kt+1 is fetched into registers while the
+// tensor cores work on tile kt; la/lb(kt, regs) load, sa/sb(kt, regs, smem) transform + store, mm(A, B) multiplies.
+// Ends with a barrier, so the caller may start another pass (or re-use shared memory) right away.
+template <class LA, class LB, class SA, class SB, class MM>
+__device__ __forceinline__ void gemm_pipeline(Smem& sm, int nkt, LA la, LB lb, SA sa, SB sb, MM mm) {
+    if (nkt <= 0) return;
+    RegTile<BM> ra;
+    RegTile<BN> rb;
+    la(0, ra);
+    lb(0, rb);
+    sa(0, ra, sm.A[0]);
+    sb(0, rb, sm.B[0]);
+    __syncthreads();
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) {
+            la(kt + 1, ra);
+            lb(kt + 1, rb);
+        }
+        mm(sm.A[buf], sm.B[buf]);
+        if (kt + 1 < nkt) {
+            sa(kt + 1, ra, sm.A[buf ^ 1]);
+            sb(kt + 1, rb, sm.B[buf ^ 1]);
+        }
+        __syncthreads();
+    }
+}
 
 __device__ __forceinline__ Smem& smem_ref() {
     extern __shared__ __align__(16) unsigned char raw[];
@@ -270,24 +381,24 @@ __global__ void __launch_bounds__(NTHR, 2) chunk_state_kernel(View4<T> X, View4<
     stage_cs(sm, 0, ws, d, b, h, c);
     __syncthreads();
     const float csQ = sm.cs[0][d.Q - 1];
-    const bool a_ifast = Bv.s3 < Bv.s1, b_ifast = X.s3 < X.s1;
+    for (int i = threadIdx.x; i < d.Q; i += NTHR)
+        sm.v1[0][i] = MODE == 0 ? exp_acc(csQ - sm.cs[0][i]) * sm.dtp[0][i] : exp_acc(sm.cs[0][i]);
+    __syncthreads();
+    const T* pa = Bv.p + b * Bv.s0 + (int64_t)l0 * Bv.s1 + g * Bv.s2 + (int64_t)n0 * Bv.s3;   // (i = n, k = s)
+    const T* pb = X.p + b * X.s0 + (int64_t)l0 * X.s1 + h * X.s2 + (int64_t)p0 * X.s3;        // (i = p, k = s)
+    const bool va = vec_ok(pa, Bv.s1, Bv.s3), vb = vec_ok(pb, X.s1, X.s3);
     Acc acc;
     acc.zero();
-    int buf = 0;
-    for (int k0 = 0; k0 < q; k0 += BK, buf ^= 1) {
-        fill_tile<BM, false>(sm.A[buf], a_ifast, [&](int i, int k) {
-            const int n = n0 + i, s = k0 + k;
-            return (n < d.N && s < q) ? Bv.at(b, l0 + s, g, n) : 0.f;
-        });
-        fill_tile<BN, false>(sm.B[buf], b_ifast, [&](int i, int k) {
-            const int p = p0 + i, s = k0 + k;
-            if (p >= d.P || s >= q) return 0.f;
-            const float w = MODE == 0 ? exp_acc(csQ - sm.cs[0][s]) * sm.dtp[0][s] : exp_acc(sm.cs[0][s]);
-            return X.at(b, l0 + s, h, p) * w;
-        });
-        __syncthreads();
-        warp_mma<false, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
-    }
+    gemm_pipeline(
+        sm, (q + BK - 1) / BK,
+        [&](int kt, RegTile<BM>& r) { load_raw<BM, false>(r, pa + (int64_t)kt * BK * Bv.s1, Bv.s3, Bv.s1, d.N - n0, q - kt * BK, va); },
+        [&](int kt, RegTile<BN>& r) { load_raw<BN, false>(r, pb + (int64_t)kt * BK * X.s1, X.s3, X.s1, d.P - p0, q - kt * BK, vb); },
+        [&](int, const RegTile<BM>& r, float* sA) { store_tile<BM, false>(sA, r, Identity()); },
+        [&](int kt, const RegTile<BN>& r, float* sB) {
+            const float* w = sm.v1[0] + kt * BK;
+            store_tile<BN, false>(sB, r, [&](int, int k, float v) { return v * w[k]; });
+        },
+        [&](const float* sA, const float* sB) { warp_mma<false, false>(acc, sA, sB, x3 != 0); });
     float* o = out + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
     for_each_acc(acc, [&](int m, int n, float& v) {
         const int nn = n0 + m, p = p0 + n;
@@ -327,22 +438,18 @@ __global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, D
     const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
     const int m0 = tm * BM, s0 = tn * BN;
     if (m0 >= q || s0 >= q || s0 > m0 + BM - 1) return;
-    const bool a_ifast = Cv.s1 <= Cv.s3, b_ifast = Bv.s1 <= Bv.s3;
+    const T* pa = Cv.p + b * Cv.s0 + (int64_t)(l0 + m0) * Cv.s1 + g * Cv.s2;   // (i = l, k = n)
+    const T* pb = Bv.p + b * Bv.s0 + (int64_t)(l0 + s0) * Bv.s1 + g * Bv.s2;   // (i = s, k = n)
+    const bool va = vec_ok(pa, Cv.s1, Cv.s3), vb = vec_ok(pb, Bv.s1, Bv.s3);
     Acc acc;
     acc.zero();
-    int buf = 0;
-    for (int k0 = 0; k0 < d.N; k0 += BK, buf ^= 1) {
-        fill_tile<BM, true>(sm.A[buf], a_ifast, [&](int i, int k) {
-            const int l = m0 + i, n = k0 + k;
-            return (l < q && n < d.N) ? Cv.at(b, l0 + l, g, n) : 0.f;
-        });
-        fill_tile<BN, true>(sm.B[buf], b_ifast, [&](int i, int k) {
-            const int s = s0 + i, n = k0 + k;
-            return (s < q && n < d.N) ? Bv.at(b, l0 + s, g, n) : 0.f;
-        });
-        __syncthreads();
-        warp_mma<true, true>(acc, sm.A[buf], sm.B[buf], x3 != 0);
-    }
+    gemm_pipeline(
+        sm, (d.N + BK - 1) / BK,
+        [&](int kt, RegTile<BM>& r) { load_raw<BM, true>(r, pa + (int64_t)kt * BK * Cv.s3, Cv.s1, Cv.s3, q - m0, d.N - kt * BK, va); },
+        [&](int kt, RegTile<BN>& r) { load_raw<BN, true>(r, pb + (int64_t)kt * BK * Bv.s3, Bv.s1, Bv.s3, q - s0, d.N - kt * BK, vb); },
+        [&](int, const RegTile<BM>& r, float* sA) { store_tile<BM, true>(sA, r, Identity()); },
+        [&](int, const RegTile<BN>& r, float* sB) { store_tile<BN, true>(sB, r, Identity()); },
+        [&](const float* sA, const float* sB) { warp_mma<true, true>(acc, sA, sB, x3 != 0); });
     float* o = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
     for_each_acc(acc, [&](int m, int n, float& v) {
         const int l = m0 + m, s = s0 + n;
@@ -351,9 +458,13 @@ __global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, D
 }
 
 // ---- K5: y = (CB o decay) (dt' x) + exp(cs) C Sin^T + D x   per (b, c, h) ------------------------
+// decay(l, s) = exp(cs_l - cs_s) is applied to the CB tile on its way into shared memory.  For rows below the
+// 32-wide k-tile it is the product of two factors <= 1 (reference point: cs at the end of the k-tile), one
+// per row and one per column, precomputed once per CTA; inside the 32 x 32 diagonal block it is evaluated
+// exactly per element (no overflow whatever the decay rate).
 template <typename T>
 __global__ void __launch_bounds__(NTHR, 2) chunk_scan_kernel(View4<T> X, View4<T> Cv, const float* D, Dims d, Ws ws, T* out,
-                                                             int64_t o0, int64_t o1, int64_t o2, int64_t o3, int x3) {
+                                                             int64_t o0, int64_t o1, int64_t o2, int64_t o3, int has_init, int x3) {
     Smem& sm = smem_ref();
     const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
     int bid = blockIdx.x;
@@ -368,40 +479,51 @@ __global__ void __launch_bounds__(NTHR, 2) chunk_scan_kernel(View4<T> X, View4<T
     if (m0 >= q) return;
     stage_cs(sm, 0, ws, d, b, h, c);
     __syncthreads();
-    const float* cb = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
-    const float* Sin = ws.states + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
-    const bool x_ifast = X.s3 < X.s1, c_ifast = Cv.s1 <= Cv.s3;
+    const int send = min(q, m0 + BM), nkt1 = (send + BK - 1) / BK;
+    for (int i = threadIdx.x; i < d.Q; i += NTHR) {
+        const float ref = sm.cs[0][min((i / BK) * BK + BK - 1, d.Q - 1)];
+        sm.v1[0][i] = exp_acc(ref - sm.cs[0][i]) * sm.dtp[0][i];   // column factor (<= dt')
+        sm.v2[0][i] = exp_acc(sm.cs[0][i]);                        // exp(cs_l) of the state term
+    }
+    for (int idx = threadIdx.x; idx < nkt1 * BM; idx += NTHR) {
+        const int kt = idx / BM, i = idx % BM;
+        const float ref = sm.cs[0][min(kt * BK + BK - 1, d.Q - 1)];
+        sm.rowf[kt][i] = exp_acc(sm.cs[0][min(m0 + i, d.Q - 1)] - ref);   // used for rows below the k-tile only (<= 1)
+    }
+    __syncthreads();
+    const float* cb = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q + (size_t)m0 * d.Q;   // (i = l, k = s)
+    const T* px = X.p + b * X.s0 + (int64_t)l0 * X.s1 + h * X.s2 + (int64_t)p0 * X.s3;                      // (i = p, k = s)
+    const bool va = vec_ok(cb, 1, d.Q), vb = vec_ok(px, X.s1, X.s3);
     Acc acc;
     acc.zero();
-    int buf = 0;
-    // diagonal block: K runs over s <= l
-    const int send = min(q, m0 + BM);
-    for (int k0 = 0; k0 < send; k0 += BK, buf ^= 1) {
-        fill_tile<BM, false>(sm.A[buf], false, [&](int i, int k) {
-            const int l = m0 + i, s = k0 + k;
-            return (l < q && s <= l) ? cb[(size_t)l * d.Q + s] * exp_acc(sm.cs[0][l] - sm.cs[0][s]) : 0.f;
-        });
-        fill_tile<BN, false>(sm.B[buf], x_ifast, [&](int i, int k) {
-            const int p = p0 + i, s = k0 + k;
-            return (p < d.P && s < q) ? X.at(b, l0 + s, h, p) * sm.dtp[0][s] : 0.f;
-        });
-        __syncthreads();
-        warp_mma<false, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
-    }
-    // off-diagonal block: contribution of the chunk-entry state
-    if (c > 0 || true) {
-        for (int k0 = 0; k0 < d.N; k0 += BK, buf ^= 1) {
-            fill_tile<BM, true>(sm.A[buf], c_ifast, [&](int i, int k) {
-                const int l = m0 + i, n = k0 + k;
-                return (l < q && n < d.N) ? Cv.at(b, l0 + l, g, n) * exp_acc(sm.cs[0][l]) : 0.f;
+    gemm_pipeline(
+        sm, nkt1,
+        [&](int kt, RegTile<BM>& r) { load_raw<BM, false>(r, cb + kt * BK, d.Q, 1, q - m0, send - kt * BK, va); },
+        [&](int kt, RegTile<BN>& r) { load_raw<BN, false>(r, px + (int64_t)kt * BK * X.s1, X.s3, X.s1, d.P - p0, q - kt * BK, vb); },
+        [&](int kt, const RegTile<BM>& r, float* sA) {
+            const int k0 = kt * BK;
+            store_tile<BM, false>(sA, r, [&](int i, int k, float v) {
+                const int l = m0 + i, s = k0 + k;
+                if (s > l) return 0.f;
+                if (l < k0 + BK) return v * exp_acc(sm.cs[0][l] - sm.cs[0][s]) * sm.dtp[0][s];
+                return v * sm.rowf[kt][i] * sm.v1[0][s];
             });
-            fill_tile<BN, false>(sm.B[buf], false, [&](int i, int k) {
-                const int p = p0 + i, n = k0 + k;
-                return (p < d.P && n < d.N) ? Sin[(size_t)p * d.N + n] : 0.f;
-            });
-            __syncthreads();
-            warp_mma<true, false>(acc, sm.A[buf], sm.B[buf], x3 != 0);
-        }
+        },
+        [&](int, const RegTile<BN>& r, float* sB) { store_tile<BN, false>(sB, r, Identity()); },
+        [&](const float* sA, const float* sB) { warp_mma<false, false>(acc, sA, sB, x3 != 0); });
+    if (c > 0 || has_init) {  // contribution of the chunk-entry state (identically zero for the first chunk without initial_states)
+        const T* pc = Cv.p + b * Cv.s0 + (int64_t)(l0 + m0) * Cv.s1 + g * Cv.s2;                                   // (i = l, k = n)
+        const float* Sin = ws.states + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N + (size_t)p0 * d.N;   // (i = p, k = n)
+        const bool vc = vec_ok(pc, Cv.s1, Cv.s3), vs = vec_ok(Sin, 1, d.N);
+        gemm_pipeline(
+            sm, (d.N + BK - 1) / BK,
+            [&](int kt, RegTile<BM>& r) { load_raw<BM, true>(r, pc + (int64_t)kt * BK * Cv.s3, Cv.s1, Cv.s3, q - m0, d.N - kt * BK, vc); },
+            [&](int kt, RegTile<BN>& r) { load_raw<BN, false>(r, Sin + kt * BK, d.N, 1, d.P - p0, d.N - kt * BK, vs); },
+            [&](int, const RegTile<BM>& r, float* sA) {
+                store_tile<BM, true>(sA, r, [&](int i, int, float v) { return v * sm.v2[0][min(m0 + i, d.Q - 1)]; });
+            },
+            [&](int, const RegTile<BN>& r, float* sB) { store_tile<BN, false>(sB, r, Identity()); },
+            [&](const float* sA, const float* sB) { warp_mma<true, false>(acc, sA, sB, x3 != 0); });
     }
     const float Dh = D ? __ldg(D + h) : 0.f;
     for_each_acc(acc, [&](int m, int n, float& v) {
@@ -863,7 +985,7 @@ static int fwd_impl(const b200_ssd_fwd_params* p, cudaStream_t st) {
     }
     LAUNCH((cb_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, Cv, Bv, d, ws, x3);
     LAUNCH((chunk_scan_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Cv, p->D, d, ws, (T*)p->out,
-           p->out_stride[0], p->out_stride[1], p->out_stride[2], p->out_stride[3], x3);
+           p->out_stride[0], p->out_stride[1], p->out_stride[2], p->out_stride[3], p->initial_states != nullptr, x3);
     return 0;
 }
 
