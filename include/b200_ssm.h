@@ -31,7 +31,7 @@ typedef void* b200_stream_t; /* cudaStream_t */
 typedef enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2 } b200_dtype;
 
 #define B200_SSCAN_MAX_DSTATE 256 /* selective_scan_common.h:11 (MAX_DSTATE) */
-#define B200_SSCAN_ROWS_PER_TASK 32
+#define B200_SSCAN_ROWS_PER_TASK 16
 
 /* ------------------------------------------------------------------------------------------
  * Mamba-1 selective scan -- replaces selective_scan_cuda.fwd / .bwd
@@ -57,8 +57,8 @@ typedef enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2 } b200_dtype;
  *
  * State checkpoints (replace the reference's chunk tensor `x`, selective_scan.cpp:313): the
  * forward writes the state entering every `ckpt_every`-th step into `ckpt`, laid out
- *   [task][chunk][n][32 rows] f32,  task = (b*G + g)*ceil((dim/G)/32) + row_tile,
- *   chunk = 1 .. ceil(L/ckpt_every)-1   (chunk 0 is the zero state and is never stored),
+ *   [task][chunk][n][16 rows, as pairs (r, r+8)] f32,  task = (b*G + g)*ceil((dim/G)/16) + row_tile,
+ *   chunk = 1 .. ceil(L/ckpt_every)-1   (chunk 0 is the zero state and is never stored); opaque to callers,
  * size from b200_sscan_ckpt_bytes().  The backward recomputes inside a chunk from its checkpoint
  * (no per-step state is ever stored).  ckpt == NULL => inference, nothing written.
  * ------------------------------------------------------------------------------------------ */
@@ -68,7 +68,7 @@ typedef struct {
     int32_t delta_softplus; /* bool */
     uint32_t rev_mask;
     int32_t u_group_div;
-    int32_t ckpt_every;     /* 8 or 16; ignored when ckpt == NULL */
+    int32_t ckpt_every;     /* 8; ignored when ckpt == NULL */
     int64_t u_batch_stride, u_group_stride, u_row_stride;
     int64_t delta_batch_stride, delta_row_stride;
     int64_t B_batch_stride, B_group_stride, B_state_stride;

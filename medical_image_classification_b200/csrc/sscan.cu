@@ -4,45 +4,63 @@
 // selective_scan_fwd_kernel.cuh:67-303, selective_scan_bwd_kernel.cuh:75-489).  Not a port: the
 // reference maps one CTA to one (batch, channel) row and runs a CUB block scan per state; here
 //
-//   * a CTA ("task") owns 32 consecutive channels of one (batch, group).  Lane = channel row,
-//     warp = a quad of states: warp w keeps states 4w..4w+3 of its 32 rows in registers, so the
-//     time recurrence is a plain in-register FFMA chain -- no block scan, no shuffles, and every
-//     exp(delta*A) is evaluated exactly once;
-//   * the group's B/C tile is staged in shared memory once per 32 rows and read back as
-//     warp-wide broadcasts (the reference re-reads B/C from L2 for every row);
-//   * u/delta tiles stream in through a double-buffered cp.async pipeline (16-byte copies when
-//     the tensors allow it) and are read back by the owning lane with conflict-free 128-bit loads
-//     (row pitch TT+4 floats);
-//   * softplus(delta + bias) is evaluated once per element by a cooperative pre-pass, not once
-//     per state;
-//   * a group can be scanned in reverse time (rev_mask) and groups can share u / dout rows
-//     (u_group_div, dout_group_div): that is all the SS2D cross-scan / cross-merge needs
-//     (MedMamba.py:393-395, 420-424), the flipped copies never exist;
-//   * backward = recompute: the forward stores the 16-float state every `ckpt_every` steps, the
-//     backward walks chunks last->first, re-derives the forward states of one chunk in registers,
-//     runs the adjoint recurrence, and reduces dB/dC over the 32 rows of the warp with a
-//     reduce-scatter butterfly before issuing one fp32 atomic per (state, step).
+//   * the unit of work ("task") is ONE WARP: 16 consecutive channels of one (batch, group), all 16 states.
+//     Lane = (state quad sq = lane >> 3, row pair i = lane & 7): the lane owns rows i and i + 8 -- carried
+//     as the two halves of packed f32x2 registers (FFMA2/FMUL2: one issue slot, two rows) -- and states
+//     4 sq .. 4 sq + 3.  The time recurrence is an in-register FFMA chain: no block scan, every
+//     exp(delta * A) is evaluated exactly once, and warps never wait for one another (no block barrier
+//     anywhere in the kernels; a CTA is just four independent tasks);
+//   * u / delta / dout tiles (16 rows x 8 steps), the group's B / C tile (16 states x 8 steps) and the
+//     8-step state checkpoint stream in through a per-warp double-buffered cp.async pipeline (16-byte
+//     copies when the tensors allow it), XOR-swizzled / padded so every shared-memory read below is
+//     conflict free;
+//   * softplus(delta + bias) (and its derivative) is evaluated once per element: each lane does the 4
+//     elements (2 rows x 2 steps) it owns and the warp all-gathers them through a 2 KB exchange tile;
+//   * reductions over states (y, d delta, d u) are 4 in-register FMAs + a 4-lane reduce-scatter, reductions
+//     over channels (dB, dC) are an in-register row-pair sum + an 8-lane reduce-scatter that leaves lane i
+//     with the total of step i: one fully used fp32 RED per (state, chunk, quantity);
+//   * a group can be scanned in reverse time (rev_mask) and groups can share u / dout rows (u_group_div,
+//     dout_group_div): that is all the SS2D cross-scan / cross-merge needs (MedMamba.py:393-395, 420-424),
+//     the flipped copies never exist.  Register arrays are indexed by MEMORY column, the scan direction is a
+//     compile-time index map;
+//   * backward = recompute: the forward stores the 16-float state entering every 8-step chunk, the backward
+//     walks chunks last -> first, re-derives the states of one chunk in registers and runs the adjoint
+//     recurrence on them.
 //
-// Binding pipes: forward = MUFU.EX2 (16 per element), backward = FP32 issue.
+// Binding pipes: forward = MUFU.EX2 (16 per element) with issue close behind, backward = issue.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int NS = 16;   // states per task pass (4 warps x 4)
-constexpr int SPW = 4;   // states per warp
-constexpr int PB = 20;   // pitch of the transposed B/C tiles [t][n] (16 + 4: 16B-aligned rows, spreads banks)
-constexpr int CKPT_EVERY = 8;  // steps between state checkpoints (== the backward chunk)
+constexpr int NS = 16;   // states per task
+constexpr int SPT = 4;   // states per thread
+constexpr int TR = B200_SSCAN_ROWS_PER_TASK;  // rows per task
+constexpr int TC = 8;    // steps per chunk == checkpoint interval
+constexpr int WPB = 1;   // warps (independent tasks) per CTA
+constexpr int EXS = 24;  // exchange tile: words per column (16 used; 24 keeps the STS.64 conflict free)
+constexpr int BCS = 40;  // B/C tile: words per state quad (4 states x 8 steps + 8 pad)
+constexpr int CKS = 80;  // checkpoint tile: words per state quad (4 states x 8 row pairs x 2 + 16 pad)
+constexpr int RDS = 144; // state-reduction tile: words per state quad (8 columns x 8 row pairs x 2 + 16 pad)
+constexpr float kLn2 = 0.6931471805599453f;
+static_assert(TR == 16, "lane mapping assumes 16 rows per task");
 
 // ---- cp.async (LDGSTS) -----------------------------------------------------------------------
 __device__ __forceinline__ void cp_async4(float* smem, const float* gmem, bool pred) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    const int n = pred ? 4 : 0;  // src-size 0 => the 4 destination bytes are zero-filled
+    const int n = pred ? 4 : 0;  // src-size 0 => the destination bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async16(float* smem, const float* gmem, bool pred) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     const int n = pred ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async16_ca(float* smem, const float* gmem, bool pred) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int n = pred ? 16 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -52,87 +70,108 @@ struct Task {
     bool rev;
 };
 
-__device__ __forceinline__ Task decode_task(const b200_sscan_fwd_params& p, int task) {
+__host__ __device__ __forceinline__ int tiles_per_group(int rpg) { return (rpg + TR - 1) / TR; }
+
+__device__ __forceinline__ Task decode_task(const b200_sscan_fwd_params& p, long long task) {
     Task t;
     t.rpg = p.dim / p.n_groups;
-    const int tiles = (t.rpg + 31) >> 5;
-    const int rt = task % tiles;
-    const int bg = task / tiles;
+    const int tiles = tiles_per_group(t.rpg);
+    const int rt = (int)(task % tiles);
+    const int bg = (int)(task / tiles);
     t.g = bg % p.n_groups;
     t.b = bg / p.n_groups;
-    t.r0 = rt * 32;
-    t.nrows = min(32, t.rpg - t.r0);
+    t.r0 = rt * TR;
+    t.nrows = min(TR, t.rpg - t.r0);
     t.d0 = t.g * t.rpg + t.r0;
     t.rev = (p.rev_mask >> t.g) & 1u;
     return t;
 }
 
-// Stage a [32 rows][TT] tile of a row-major activation tensor into shared memory in MEMORY order:
-// column c <-> sequence position l_lo + c.  fp32 goes through cp.async (asynchronous; 16-byte copies
-// when `vec`), 16-bit types are converted on the fly (synchronous).  Out-of-range elements become 0.
-// NTHR is a compile-time constant so the index arithmetic folds away.
-template <typename T, int TT, int NTHR>
-__device__ __forceinline__ void stage_rows(float* tile, const T* base, int64_t row_stride, int nrows, int l_lo, int L,
-                                           bool vec, int tid) {
-    constexpr int TP = TT + 4;
-    if constexpr (sizeof(T) == 4) {
-        if (vec) {
-#pragma unroll
-            for (int idx0 = 0; idx0 < 32 * (TT / 4); idx0 += NTHR) {
-                const int idx = idx0 + tid;
-                if ((32 * (TT / 4)) % NTHR != 0 && idx >= 32 * (TT / 4)) break;
-                const int rr = idx / (TT / 4), c = (idx % (TT / 4)) * 4;
-                const int l = l_lo + c;
-                const bool ok = rr < nrows && l >= 0 && l < L;  // L % 4 == 0 and l_lo % 4 == 0: all-or-nothing
-                cp_async16(tile + rr * TP + c, ok ? (const float*)base + (size_t)rr * row_stride + l : (const float*)base, ok);
-            }
-        } else {
-#pragma unroll
-            for (int idx0 = 0; idx0 < 32 * TT; idx0 += NTHR) {
-                const int idx = idx0 + tid;
-                const int rr = idx / TT, c = idx % TT;
-                const int l = l_lo + c;
-                const bool ok = rr < nrows && l >= 0 && l < L;
-                cp_async4(tile + rr * TP + c, ok ? (const float*)base + (size_t)rr * row_stride + l : (const float*)base, ok);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int idx0 = 0; idx0 < 32 * TT; idx0 += NTHR) {
-            const int idx = idx0 + tid;
-            const int rr = idx / TT, c = idx % TT;
-            const int l = l_lo + c;
-            const bool ok = rr < nrows && l >= 0 && l < L;
-            tile[rr * TP + c] = ok ? ldg_stream(base + (size_t)rr * row_stride + l) : 0.f;
-        }
-    }
+// ---- shared-memory tile layouts -------------------------------------------------------------------
+// raw activation tile: 16 rows x 8 steps, pitch 8, the two 16-byte halves of a row swapped on rows 4-7 / 12-15
+__device__ __forceinline__ int raw_pos(int row, int c) { return row * TC + (c ^ (((row >> 2) & 1) << 2)); }
+// B / C tile: [state quad][state in quad][8 steps], quads 40 words apart
+__device__ __forceinline__ int bc_pos(int n, int c) { return (n >> 2) * BCS + (n & 3) * TC + c; }
+
+// One 16-byte cp.async per lane and chunk moves a whole [16 rows or states][8 steps] fp32 tile.  Everything that
+// does not depend on the chunk (source row pointer, shared-memory slot, row validity) is computed once per task.
+struct Stager {
+    const float* src;   // this lane's row at sequence position 0
+    unsigned dst;       // shared address of the lane's 16-byte slot in stage 0
+    bool ok;
+};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_s(unsigned dst, const float* src, bool pred, bool ca) {
+    const int n = pred ? 16 : 0;
+    if (ca) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ Stager make_row_stager(float* tile, const float* base, int64_t row_stride, int nrows, int lane) {
+    const int row = lane >> 1, c = (lane & 1) * 4;
+    Stager s;
+    s.ok = row < nrows;
+    s.src = base + (s.ok ? (size_t)row * row_stride : 0);
+    s.dst = smem_u32(tile + raw_pos(row, c));
+    return s;
+}
+__device__ __forceinline__ Stager make_bc_stager(float* tile, const float* base, int64_t state_stride, int N, int lane) {
+    const int n = lane >> 1, c = (lane & 1) * 4;
+    Stager s;
+    s.ok = n < N;
+    s.src = base + (s.ok ? (size_t)n * state_stride : 0);
+    s.dst = smem_u32(tile + bc_pos(n, c));
+    return s;
+}
+// l = l_lo + this lane's first column; the 4 positions are all inside or all outside [0, L) (L % 4 == 0)
+__device__ __forceinline__ void stage16(const Stager& s, unsigned stage_off, int l, int L, bool ca) {
+    const bool ok = s.ok && (unsigned)l < (unsigned)L;
+    cp_async16_s(s.dst + stage_off, ok ? s.src + l : s.src, ok, ca);
 }
 
-// Stage the group's [N][TT] slice of B or C transposed to [TT][PB] (state index fastest).
-template <typename T, int TT, int NTHR>
-__device__ __forceinline__ void stage_bc(float* tile, const T* base, int64_t state_stride, int N, int l_lo, int L, int tid) {
-#pragma unroll
-    for (int idx0 = 0; idx0 < NS * TT; idx0 += NTHR) {
-        const int idx = idx0 + tid;
-        const int n = idx / TT, c = idx % TT;
+// Element-wise fallbacks (L % 4 != 0 or unaligned views): column c <-> sequence position l_lo + c; out-of-range -> 0.
+__device__ __forceinline__ void stage_rows_slow(float* tile, const float* base, int64_t row_stride, int nrows, int l_lo, int L, int lane) {
+#pragma unroll 1
+    for (int k = 0; k < TR * TC / 32; ++k) {
+        const int idx = k * 32 + lane;
+        const int row = idx >> 3, c = idx & 7;
+        const int l = l_lo + c;
+        const bool ok = row < nrows && l >= 0 && l < L;
+        cp_async4(tile + raw_pos(row, c), ok ? base + (size_t)row * row_stride + l : base, ok);
+    }
+}
+__device__ __forceinline__ void stage_bc_slow(float* tile, const float* base, int64_t state_stride, int N, int l_lo, int L, int lane) {
+#pragma unroll 1
+    for (int k = 0; k < NS * TC / 32; ++k) {
+        const int idx = k * 32 + lane;
+        const int n = idx >> 3, c = idx & 7;
         const int l = l_lo + c;
         const bool ok = n < N && l >= 0 && l < L;
-        if constexpr (sizeof(T) == 4) {
-            cp_async4(tile + c * PB + n, ok ? (const float*)base + (size_t)n * state_stride + l : (const float*)base, ok);
-        } else {
-            tile[c * PB + n] = ok ? to_f32<T>(__ldg(base + (size_t)n * state_stride + l)) : 0.f;
-        }
+        cp_async4(tile + bc_pos(n, c), ok ? base + (size_t)n * state_stride + l : base, ok);
     }
 }
 
-template <bool REV> __device__ __forceinline__ float4 ld4(const float* p) {
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    return REV ? make_float4(v.w, v.z, v.y, v.x) : v;
+// Synchronous variants for 16-bit I/O (converted on the fly).
+template <typename T>
+__device__ __forceinline__ void fill_bc_sync(float* tile, const T* base, int64_t state_stride, int N, int l_lo, int L, int lane) {
+#pragma unroll
+    for (int k = 0; k < NS * TC / 32; ++k) {
+        const int idx = k * 32 + lane;
+        const int n = idx >> 3, c = idx & 7;
+        const int l = l_lo + c;
+        const bool ok = n < N && l >= 0 && l < L;
+        tile[bc_pos(n, c)] = ok ? to_f32<T>(__ldg(base + (size_t)n * state_stride + l)) : 0.f;
+    }
 }
-template <bool REV> __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) {
-    *reinterpret_cast<float4*>(p) = REV ? make_float4(d, c, b, a) : make_float4(a, b, c, d);
+
+// One chunk of checkpoints (256 floats, [n][row pair][2]) -> padded tile.
+__device__ __forceinline__ void stage_ckpt(float* tile, const float* src, int lane) {
+#pragma unroll
+    for (int k0 = 0; k0 < NS * TR / 4; k0 += 32) {
+        const int k = k0 + lane;
+        const int n = k >> 2, part = k & 3;
+        cp_async16(tile + (n >> 2) * CKS + (n & 3) * 16 + part * 4, src + k * 4, true);
+    }
 }
-__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
 
 template <typename T>
 __device__ __forceinline__ bool can_vectorize(const void* p, int64_t row_stride, int64_t batch_stride, int64_t group_stride,
@@ -141,44 +180,101 @@ __device__ __forceinline__ bool can_vectorize(const void* p, int64_t row_stride,
            (reinterpret_cast<uintptr_t>(p) & 15) == 0;
 }
 
+// two adjacent sequence positions of one row
+template <typename T> __device__ __forceinline__ void store_pair(T* p, float a, float b, bool ok0, bool ok1, bool vec) {
+    if (vec && ok0 && ok1) {
+        if constexpr (sizeof(T) == 4) {
+            __stcs(reinterpret_cast<float2*>(p), make_float2(a, b));
+        } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+            __stcs(reinterpret_cast<unsigned int*>(p), *reinterpret_cast<const unsigned int*>(&v));
+        } else {
+            const __half2 v = __floats2half2_rn(a, b);
+            __stcs(reinterpret_cast<unsigned int*>(p), *reinterpret_cast<const unsigned int*>(&v));
+        }
+    } else {
+        if (ok0) stg_stream(p, a);
+        if (ok1) stg_stream(p + 1, b);
+    }
+}
+template <typename T> __device__ __forceinline__ bool pair_vec_ok(const void* p, int64_t row_stride, int64_t batch_stride, int L) {
+    return (L & 1) == 0 && (row_stride & 1) == 0 && (batch_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(p) & (2 * sizeof(T) - 1)) == 0;
+}
+
+__device__ __forceinline__ float2 ex2_2(float2 e) { return make_float2(ex2(e.x), ex2(e.y)); }
+
+// ---- warp reductions -----------------------------------------------------------------------------
+// Reduce-scatter of 8 per-lane values over the 8 lanes that share a state quad (lane bits 0-2): lane i ends
+// with the 8-lane total of v[i].  7 shuffles instead of 24.
+__device__ __forceinline__ float rs8_rows(const float (&v)[8], int lane) {
+    float h4[4], h2[2];
+    const bool u4 = lane & 4, u2 = lane & 2, u1 = lane & 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float keep = u4 ? v[k + 4] : v[k], send = u4 ? v[k] : v[k + 4];
+        h4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float keep = u2 ? h4[k + 2] : h4[k], send = u2 ? h4[k] : h4[k + 2];
+        h2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float keep = u1 ? h2[1] : h2[0], send = u1 ? h2[0] : h2[1];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// Sum 8 per-lane row-pair values over the 4 state quads (lane bits 3-4) through a 2.3 KB shared-memory tile: the
+// lane ends with the totals of columns 2 sq and 2 sq + 1 -- the two columns whose elements it owns in the
+// prologue / epilogue.  8 STS.64 + 8 LDS.64 + 6 packed adds (a shuffle reduce-scatter costs ~100 issue slots).
+// The tile layout [quad][column][row pair] is padded (RDS) and XOR-skewed so both phases are conflict free.
+__device__ __forceinline__ int rd_pos(int quad, int cc, int i) { return quad * RDS + ((cc * 16 + 2 * i) ^ (((cc >> 1) & 1) << 4)); }
+__device__ __forceinline__ void reduce_states(float* tile, const float2 (&v)[8], int lane, float2& r0, float2& r1) {
+    const int sq = lane >> 3, i = lane & 7;
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<float2*>(tile + rd_pos(sq, cc, i)) = v[cc];
+    __syncwarp();
+    const int c0 = 2 * sq;
+    r0 = *reinterpret_cast<const float2*>(tile + rd_pos(0, c0, i));
+    r1 = *reinterpret_cast<const float2*>(tile + rd_pos(0, c0 + 1, i));
+#pragma unroll
+    for (int qd = 1; qd < 4; ++qd) {
+        r0 = __fadd2_rn(r0, *reinterpret_cast<const float2*>(tile + rd_pos(qd, c0, i)));
+        r1 = __fadd2_rn(r1, *reinterpret_cast<const float2*>(tile + rd_pos(qd, c0 + 1, i)));
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // forward
 // ----------------------------------------------------------------------------------------------
-template <int TT>
-struct FwdSmem {
-    static constexpr int TP = TT + 4;
-    float u[2][32 * TP];     // raw u tiles (double buffered)
-    float d[2][32 * TP];     // raw delta tiles -> softplus(delta + bias) in place
-    float B[2][TT * PB];     // [c][n]
-    float C[2][TT * PB];
-    float du[32 * TP];       // delta' * u
-    float y[4][32 * TP];     // per-warp partial outputs
-    float bias[32], D[32];
+struct FwdWarpSmem {
+    float raw[2][2][TR * TC];      // [stage][u, delta]
+    float bc[2][2][4 * BCS];       // [stage][B, C]
+    float ex[2][TC * EXS];         // delta' | delta' * u, [column][row pair][2]
+    float rd[4 * RDS];             // reduction over the state quads
 };
 
-template <typename T, int TT, int NW, bool HAS_Z, bool REV>
-__device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, const Task& t, FwdSmem<TT>& sm) {
-    constexpr int TP = FwdSmem<TT>::TP;
-    constexpr int NTHR = NW * 32;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, w = tid >> 5;
+template <typename T, bool HAS_Z, bool REV>
+__device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, const Task& t, long long task, FwdWarpSmem& sm,
+                                               int lane) {
+    constexpr bool ASYNC = sizeof(T) == 4;
+    const int sq = lane >> 3, i = lane & 7;
     const int L = p.seqlen, N = p.dstate;
-    const bool row_ok = lane < t.nrows;
-    const int d_lane = t.d0 + lane;
+    const int c0 = 2 * sq;  // this lane's two columns in the prologue / epilogue
+    const bool okA = i < t.nrows, okB = i + 8 < t.nrows;
+    const int dA_ = t.d0 + i, dB_ = t.d0 + i + 8;
 
-    // this warp's 4 states as two packed pairs
-    float2 A2[2], x[2];
+    float2 A2[SPT], x[SPT];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int n = w * SPW + 2 * j;
-        A2[j].x = (row_ok && n < N) ? __ldg(p.A + (size_t)d_lane * N + n) * kLog2e : 0.f;
-        A2[j].y = (row_ok && n + 1 < N) ? __ldg(p.A + (size_t)d_lane * N + n + 1) * kLog2e : 0.f;
+    for (int j = 0; j < SPT; ++j) {
+        const int n = sq * SPT + j;
+        A2[j].x = (okA && n < N) ? __ldg(p.A + (size_t)dA_ * N + n) * kLog2e : 0.f;
+        A2[j].y = (okB && n < N) ? __ldg(p.A + (size_t)dB_ * N + n) * kLog2e : 0.f;
         x[j] = make_float2(0.f, 0.f);
     }
-    if (tid < 32) {
-        sm.D[tid] = (p.D && row_ok) ? __ldg(p.D + d_lane) : 0.f;
-        sm.bias[tid] = (p.delta_bias && row_ok) ? __ldg(p.delta_bias + d_lane) : 0.f;
-    }
+    const float biasA = (p.delta_bias && okA) ? __ldg(p.delta_bias + dA_) : 0.f;
+    const float biasB = (p.delta_bias && okB) ? __ldg(p.delta_bias + dB_) : 0.f;
+    const float DA = (p.D && okA) ? __ldg(p.D + dA_) : 0.f;
+    const float DB = (p.D && okB) ? __ldg(p.D + dB_) : 0.f;
     const bool softplus = p.delta_softplus != 0;
 
     const T* u_base = (const T*)p.u + (size_t)t.b * p.u_batch_stride + (size_t)(t.g / p.u_group_div) * p.u_group_stride +
@@ -190,230 +286,198 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
     const T* C_base = (const T*)p.C + (size_t)t.b * p.C_batch_stride + (size_t)t.g * p.C_group_stride;
     const bool vec_u = can_vectorize<T>(p.u, p.u_row_stride, p.u_batch_stride, p.u_group_stride, L);
     const bool vec_d = can_vectorize<T>(p.delta, p.delta_row_stride, p.delta_batch_stride, 0, L);
-    const bool vec_o = can_vectorize<T>(p.out, p.out_row_stride, p.out_batch_stride, 0, L) && !HAS_Z;
+    const bool vec_B = can_vectorize<T>(p.B, p.B_state_stride, p.B_batch_stride, p.B_group_stride, L);
+    const bool vec_C = can_vectorize<T>(p.C, p.C_state_stride, p.C_batch_stride, p.C_group_stride, L);
+    const bool vec_o = pair_vec_ok<T>(p.out, p.out_row_stride, p.out_batch_stride, L);
 
-    const int nck = p.ckpt ? (L + CKPT_EVERY - 1) / CKPT_EVERY : 0;
-    float* ck = p.ckpt ? p.ckpt + (size_t)blockIdx.x * (size_t)(nck - 1) * NS * 32 : nullptr;
+    const int nck = (L + TC - 1) / TC;
+    float* ck = p.ckpt ? p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR : nullptr;
 
-    const int ntiles = (L + TT - 1) / TT;
-    auto l_lo_of = [&](int tile) { return REV ? L - (tile + 1) * TT : tile * TT; };
-    auto prefetch = [&](int tile) {
-        if (tile < ntiles) {
-            const int buf = tile & 1, l_lo = l_lo_of(tile);
-            stage_rows<T, TT, NTHR>(sm.u[buf], u_base, p.u_row_stride, t.nrows, l_lo, L, vec_u, tid);
-            stage_rows<T, TT, NTHR>(sm.d[buf], d_base, p.delta_row_stride, t.nrows, l_lo, L, vec_d, tid);
-            stage_bc<T, TT, NTHR>(sm.B[buf], B_base, p.B_state_stride, N, l_lo, L, tid);
-            stage_bc<T, TT, NTHR>(sm.C[buf], C_base, p.C_state_stride, N, l_lo, L, tid);
+    auto l_lo_of = [&](int c) { return REV ? L - (c + 1) * TC : c * TC; };
+    const bool fast = vec_u && vec_d && vec_B && vec_C;
+    const Stager su = make_row_stager(sm.raw[0][0], (const float*)u_base, p.u_row_stride, t.nrows, lane);
+    const Stager sd = make_row_stager(sm.raw[0][1], (const float*)d_base, p.delta_row_stride, t.nrows, lane);
+    const Stager sB = make_bc_stager(sm.bc[0][0], (const float*)B_base, p.B_state_stride, N, lane);
+    const Stager sC = make_bc_stager(sm.bc[0][1], (const float*)C_base, p.C_state_stride, N, lane);
+    const int lc = (lane & 1) * 4;
+    auto prefetch = [&](int c) {
+        if (ASYNC) {
+            if (c < nck) {
+                const int buf = c & 1, l_lo = l_lo_of(c);
+                if (fast) {
+                    const int l = l_lo + lc;
+                    stage16(su, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    stage16(sd, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    stage16(sB, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
+                    stage16(sC, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
+                } else {
+                    stage_rows_slow(sm.raw[buf][0], (const float*)u_base, p.u_row_stride, t.nrows, l_lo, L, lane);
+                    stage_rows_slow(sm.raw[buf][1], (const float*)d_base, p.delta_row_stride, t.nrows, l_lo, L, lane);
+                    stage_bc_slow(sm.bc[buf][0], (const float*)B_base, p.B_state_stride, N, l_lo, L, lane);
+                    stage_bc_slow(sm.bc[buf][1], (const float*)C_base, p.C_state_stride, N, l_lo, L, lane);
+                }
+            }
+            cp_async_commit();  // (possibly empty) group: keeps the wait_group arithmetic uniform
         }
-        cp_async_commit();  // (possibly empty) group: keeps the wait_group arithmetic uniform
     };
     prefetch(0);
     prefetch(1);
 
-    for (int tile = 0; tile < ntiles; ++tile) {
-        const int buf = tile & 1;
-        const int s0 = tile * TT;
-        const int nv = min(TT, L - s0);
-        const int l_lo = l_lo_of(tile);
-        cp_async_wait<1>();
-        __syncthreads();  // (1) tile landed; previous tile's output store finished reading sm.y
-        // ---- pre-pass: delta' = softplus(delta + bias) once per element; du = delta' * u ----
-#pragma unroll
-        for (int idx0 = 0; idx0 < 32 * (TT / 4); idx0 += NTHR) {
-            const int idx = idx0 + tid;
-            const int rr = idx / (TT / 4), c = (idx % (TT / 4)) * 4;
-            const float4 dr = *reinterpret_cast<const float4*>(&sm.d[buf][rr * TP + c]);
-            const float4 ur = *reinterpret_cast<const float4*>(&sm.u[buf][rr * TP + c]);
-            const float bias = sm.bias[rr];
-            const float draw[4] = {dr.x, dr.y, dr.z, dr.w};
-            const float uraw[4] = {ur.x, ur.y, ur.z, ur.w};
-            float dl[4], dq[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int l = l_lo + c + k;
-                float v = draw[k] + bias;
-                if (softplus) v = softplus_sigmoid(v).sp;
-                if (l < 0 || l >= L) v = 0.f;  // out-of-range steps become the identity: a = 1, b = 0
-                dl[k] = v;
-                dq[k] = v * uraw[k];
-            }
-            *reinterpret_cast<float4*>(&sm.d[buf][rr * TP + c]) = make_float4(dl[0], dl[1], dl[2], dl[3]);
-            *reinterpret_cast<float4*>(&sm.du[rr * TP + c]) = make_float4(dq[0], dq[1], dq[2], dq[3]);
-        }
-        __syncthreads();  // (2)
-        // ---- recurrence: lane = row, this warp's 4 states (2 packed pairs), 4 steps per iteration ----
-        const float Dv = (w == 0) ? sm.D[lane] : 0.f;
-#pragma unroll
-        for (int i4 = 0; i4 < TT / 4; ++i4) {
-            const int cb = REV ? TT - 4 - 4 * i4 : 4 * i4;  // memory-order column of this step quad
-            if (i4 * 4 < nv) {                              // warp-uniform
-                const int sb = s0 + i4 * 4;
-                if ((i4 & 1) == 0 && ck != nullptr && sb > 0) {  // sb % CKPT_EVERY == 0
-                    float* dst = ck + ((size_t)(sb / CKPT_EVERY - 1) * NS + w * SPW) * 32 + lane;
-                    dst[0] = x[0].x; dst[32] = x[0].y; dst[64] = x[1].x; dst[96] = x[1].y;
-                }
-                const float4 d4 = ld4<REV>(&sm.d[buf][lane * TP + cb]);
-                const float4 q4 = ld4<REV>(&sm.du[lane * TP + cb]);
-                float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (w == 0) u4 = ld4<REV>(&sm.u[buf][lane * TP + cb]);
-                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-                const float dq[4] = {q4.x, q4.y, q4.z, q4.w};
-                const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-                float yy[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int c = REV ? TT - 1 - (i4 * 4 + k) : i4 * 4 + k;
-                    const float4 b4 = *reinterpret_cast<const float4*>(&sm.B[buf][c * PB + w * SPW]);
-                    const float4 c4 = *reinterpret_cast<const float4*>(&sm.C[buf][c * PB + w * SPW]);
-                    const float2 d2 = dup2(dd[k]), q2 = dup2(dq[k]);
-                    const float2 e0 = __fmul2_rn(d2, A2[0]), e1 = __fmul2_rn(d2, A2[1]);
-                    const float2 a0 = make_float2(ex2(e0.x), ex2(e0.y)), a1 = make_float2(ex2(e1.x), ex2(e1.y));
-                    x[0] = __ffma2_rn(a0, x[0], __fmul2_rn(q2, make_float2(b4.x, b4.y)));
-                    x[1] = __ffma2_rn(a1, x[1], __fmul2_rn(q2, make_float2(b4.z, b4.w)));
-                    float2 y2 = __fmul2_rn(make_float2(c4.x, c4.y), x[0]);
-                    y2 = __ffma2_rn(make_float2(c4.z, c4.w), x[1], y2);
-                    yy[k] = fmaf(Dv, uu[k], y2.x + y2.y);
-                }
-                st4<REV>(&sm.y[w][lane * TP + cb], yy[0], yy[1], yy[2], yy[3]);
-            }
-        }
-        __syncthreads();  // (3) partial outputs ready; raw buffers of this tile are dead
-        prefetch(tile + 2);
-        // ---- out = sum of the warps' partials (* silu(z)), written at its memory position ----
-        if (vec_o) {
-#pragma unroll
-            for (int idx0 = 0; idx0 < 32 * (TT / 4); idx0 += NTHR) {
-                const int idx = idx0 + tid;
-                const int rr = idx / (TT / 4), c = (idx % (TT / 4)) * 4;
-                const int l = l_lo + c;
-                if (rr < t.nrows && l >= 0 && l < L) {
-                    float4 v = *reinterpret_cast<const float4*>(&sm.y[0][rr * TP + c]);
-#pragma unroll
-                    for (int ww = 1; ww < NW; ++ww) {
-                        const float4 o = *reinterpret_cast<const float4*>(&sm.y[ww][rr * TP + c]);
-                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                    }
-                    __stcs(reinterpret_cast<float4*>((float*)o_base + (size_t)rr * p.out_row_stride + l), v);
-                }
-            }
+    for (int c = 0; c < nck; ++c) {
+        const int buf = c & 1;
+        const int l_lo = l_lo_of(c);
+        const int la = l_lo + c0;  // sequence position of this lane's first column
+        const bool v0 = la >= 0 && la < L, v1 = la + 1 >= 0 && la + 1 < L;
+        float uA[2], uB[2], dlA[2], dlB[2];
+        if (ASYNC) {
+            cp_async_wait<1>();
+            __syncwarp();
+            const float2 ua = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i, c0)]);
+            const float2 ub = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i + 8, c0)]);
+            const float2 da = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i, c0)]);
+            const float2 db = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i + 8, c0)]);
+            uA[0] = ua.x; uA[1] = ua.y; uB[0] = ub.x; uB[1] = ub.y;
+            dlA[0] = da.x; dlA[1] = da.y; dlB[0] = db.x; dlB[1] = db.y;
         } else {
+            fill_bc_sync<T>(sm.bc[buf][0], B_base, p.B_state_stride, N, l_lo, L, lane);
+            fill_bc_sync<T>(sm.bc[buf][1], C_base, p.C_state_stride, N, l_lo, L, lane);
 #pragma unroll
-            for (int idx0 = 0; idx0 < 32 * TT; idx0 += NTHR) {
-                const int idx = idx0 + tid;
-                const int rr = idx / TT, c = idx % TT;
-                const int l = l_lo + c;
-                if (rr < t.nrows && l >= 0 && l < L) {
-                    float v = sm.y[0][rr * TP + c];
-#pragma unroll
-                    for (int ww = 1; ww < NW; ++ww) v += sm.y[ww][rr * TP + c];
-                    if (HAS_Z) {
-                        const float zz = ldg_stream(z_base + (size_t)rr * p.z_row_stride + l);
-                        v *= zz * sigmoidf_(zz);
-                    }
-                    stg_stream(o_base + (size_t)rr * p.out_row_stride + l, v);
-                }
+            for (int e = 0; e < 2; ++e) {
+                const bool v = e ? v1 : v0;
+                uA[e] = (okA && v) ? ldg_stream(u_base + (size_t)i * p.u_row_stride + la + e) : 0.f;
+                uB[e] = (okB && v) ? ldg_stream(u_base + (size_t)(i + 8) * p.u_row_stride + la + e) : 0.f;
+                dlA[e] = (okA && v) ? ldg_stream(d_base + (size_t)i * p.delta_row_stride + la + e) : 0.f;
+                dlB[e] = (okB && v) ? ldg_stream(d_base + (size_t)(i + 8) * p.delta_row_stride + la + e) : 0.f;
             }
         }
-    }
-    cp_async_wait<0>();
-    if (p.last_state != nullptr && row_ok) {
-        float* ls = p.last_state + ((size_t)t.b * p.dim + d_lane) * N;
-        const float xs[4] = {x[0].x, x[0].y, x[1].x, x[1].y};
+        // ---- prologue: delta' = softplus(delta + bias) once per element; q = delta' * u ----
 #pragma unroll
-        for (int j = 0; j < SPW; ++j)
-            if (w * SPW + j < N) ls[w * SPW + j] = xs[j];
+        for (int e = 0; e < 2; ++e) {
+            const bool v = e ? v1 : v0;
+            float a = dlA[e] + biasA, b = dlB[e] + biasB;
+            if (softplus) { a = softplus_sigmoid(a).sp; b = softplus_sigmoid(b).sp; }
+            dlA[e] = (okA && v) ? a : 0.f;  // out-of-range steps / rows become the identity: decay 1, input 0
+            dlB[e] = (okB && v) ? b : 0.f;
+            *reinterpret_cast<float2*>(&sm.ex[0][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e], dlB[e]);
+            *reinterpret_cast<float2*>(&sm.ex[1][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e] * uA[e], dlB[e] * uB[e]);
+        }
+        __syncwarp();
+        float2 dl2[TC], q2[TC], y2[TC];
+#pragma unroll
+        for (int cc = 0; cc < TC; ++cc) {
+            dl2[cc] = *reinterpret_cast<const float2*>(&sm.ex[0][cc * EXS + 2 * i]);
+            q2[cc] = *reinterpret_cast<const float2*>(&sm.ex[1][cc * EXS + 2 * i]);
+            y2[cc] = make_float2(0.f, 0.f);
+        }
+        // ---- recurrence: this lane's 4 states, one after the other, 2 rows per packed instruction ----
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+            const int n = sq * SPT + j;
+            if (ck != nullptr && c > 0) *reinterpret_cast<float2*>(ck + (size_t)(c - 1) * NS * TR + n * TR + 2 * i) = x[j];
+            float Bv[TC], Cv[TC];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&sm.bc[buf][0][sq * BCS + j * TC + hh * 4]);
+                const float4 c4 = *reinterpret_cast<const float4*>(&sm.bc[buf][1][sq * BCS + j * TC + hh * 4]);
+                Bv[hh * 4] = b4.x; Bv[hh * 4 + 1] = b4.y; Bv[hh * 4 + 2] = b4.z; Bv[hh * 4 + 3] = b4.w;
+                Cv[hh * 4] = c4.x; Cv[hh * 4 + 1] = c4.y; Cv[hh * 4 + 2] = c4.z; Cv[hh * 4 + 3] = c4.w;
+            }
+            float2 xs = x[j];
+#pragma unroll
+            for (int s = 0; s < TC; ++s) {
+                const int cc = REV ? TC - 1 - s : s;
+                const float2 a = ex2_2(__fmul2_rn(dl2[cc], A2[j]));
+                const float2 qB = make_float2(q2[cc].x * Bv[cc], q2[cc].y * Bv[cc]);
+                xs = __ffma2_rn(a, xs, qB);
+                y2[cc].x = fmaf(Cv[cc], xs.x, y2[cc].x);
+                y2[cc].y = fmaf(Cv[cc], xs.y, y2[cc].y);
+            }
+            x[j] = xs;
+        }
+        // ---- out = sum over states (4 lanes) + D u (* silu(z)), written at its memory position ----
+        float2 r0, r1;
+        reduce_states(sm.rd, y2, lane, r0, r1);
+        float oA[2] = {fmaf(DA, uA[0], r0.x), fmaf(DA, uA[1], r1.x)};
+        float oB[2] = {fmaf(DB, uB[0], r0.y), fmaf(DB, uB[1], r1.y)};
+        if (HAS_Z) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool v = e ? v1 : v0;
+                if (okA && v) { const float zz = ldg_stream(z_base + (size_t)i * p.z_row_stride + la + e); oA[e] *= zz * sigmoidf_(zz); }
+                if (okB && v) { const float zz = ldg_stream(z_base + (size_t)(i + 8) * p.z_row_stride + la + e); oB[e] *= zz * sigmoidf_(zz); }
+            }
+        }
+        store_pair<T>(o_base + (size_t)i * p.out_row_stride + la, oA[0], oA[1], okA && v0, okA && v1, vec_o);
+        store_pair<T>(o_base + (size_t)(i + 8) * p.out_row_stride + la, oB[0], oB[1], okB && v0, okB && v1, vec_o);
+        __syncwarp();  // every lane is done with this chunk's tiles
+        prefetch(c + 2);
+    }
+    if (ASYNC) cp_async_wait<0>();
+    if (p.last_state != nullptr) {
+#pragma unroll
+        for (int j = 0; j < SPT; ++j) {
+            const int n = sq * SPT + j;
+            if (n < N) {
+                if (okA) p.last_state[((size_t)t.b * p.dim + dA_) * N + n] = x[j].x;
+                if (okB) p.last_state[((size_t)t.b * p.dim + dB_) * N + n] = x[j].y;
+            }
+        }
     }
 }
 
-template <typename T, int TT, int NW, bool HAS_Z>
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? 6 : 8) sscan_fwd_kernel(const __grid_constant__ b200_sscan_fwd_params p) {
-    __shared__ __align__(16) FwdSmem<TT> sm;
-    const Task t = decode_task(p, blockIdx.x);
-    if (t.rev) sscan_fwd_body<T, TT, NW, HAS_Z, true>(p, t, sm);
-    else sscan_fwd_body<T, TT, NW, HAS_Z, false>(p, t, sm);
+template <typename T, bool HAS_Z>
+__global__ void __launch_bounds__(WPB * 32, 16) sscan_fwd_kernel(const __grid_constant__ b200_sscan_fwd_params p, long long n_tasks) {
+    __shared__ __align__(16) FwdWarpSmem sm;
+    static_assert(WPB == 1, "one warp-task per CTA");
+    const int lane = threadIdx.x;
+    const long long task = blockIdx.x;
+    (void)n_tasks;
+    const Task t = decode_task(p, task);
+    if (t.rev) sscan_fwd_body<T, HAS_Z, true>(p, t, task, sm, lane);
+    else sscan_fwd_body<T, HAS_Z, false>(p, t, task, sm, lane);
 }
 
 // ----------------------------------------------------------------------------------------------
 // backward
 // ----------------------------------------------------------------------------------------------
-// Sum v[0..TC) over the 32 lanes of the warp with a reduce-scatter butterfly: each halving step
-// exchanges half of the remaining values, so the whole reduction costs ~TC shuffles instead of
-// 5*TC.  On return every lane holds the 32-row total of item `rs_item<TC>(lane)`.
-template <int TC> __device__ __forceinline__ int rs_item(int lane);
-template <> __device__ __forceinline__ int rs_item<8>(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
-
-template <int M> __device__ __forceinline__ float rs_step(float (&v)[M], int lane, int bit) {
-    // M values -> M/2 values across the lane pair (lane ^ bit); lanes with `bit` set keep the upper half
-    const bool up = (lane & bit) != 0;
-    if constexpr (M == 1) {
-        return v[0];
-    } else {
-        float h[M / 2];
-#pragma unroll
-        for (int j = 0; j < M / 2; ++j) {
-            const float keep = up ? v[j + M / 2] : v[j];
-            const float send = up ? v[j] : v[j + M / 2];
-            h[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-        }
-        return rs_step<M / 2>(h, lane, bit >> 1);
-    }
-}
-
-template <int TC> __device__ __forceinline__ float reduce_scatter(float (&v)[TC], int lane) {
-    static_assert(TC == 8, "reduce_scatter is instantiated for 8-step chunks");
-    float r = rs_step<TC>(v, lane, 16);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
-}
-
-template <int TC, bool HAS_Z>
-struct BwdSmem {
-    static constexpr int TP = TC + 4;
-    static constexpr int SP = (HAS_Z ? 3 : 2) * TC + 4;  // pitch of the per-warp partial sums
-    float u[2][32 * TP];    // u tile
-    float d[2][32 * TP];    // raw delta tile -> delta' in place
-    float g[2][32 * TP];    // dout tile -> dout * silu(z) in place
-    float z[HAS_Z ? 2 : 1][HAS_Z ? 32 * TP : 4];  // z tile -> dout * d silu(z)/dz in place
-    float B[2][TC * PB];
-    float C[2][TC * PB];
-    float ck[2][NS * 32];   // state entering the chunk, [n][lane]
-    float sg[32 * TP];      // sigmoid(delta + bias) = d softplus: chain-rule factor of ddelta
-    float part[4][32 * SP]; // per-warp partial s1 | s2 (| y) in memory-order columns
-    float bias[32], D[32];
+struct BwdWarpSmem {
+    float raw[2][3][TR * TC];   // [stage][u, delta -> sigmoid(delta + bias), dout]
+    float bc[2][2][4 * BCS];    // [stage][B, C]
+    float ck[2][4 * CKS];       // state entering the chunk
+    float ex[3][TC * EXS];      // delta' | delta' * u | gated dout, [column][row pair][2]
+    float rd[2][4 * RDS];       // reductions over the state quads
+    float2 A2[SPT][32];         // per-lane constants / accumulators that would not fit in registers:
+    float2 dA[SPT][32];         // A * log2(e) and the running dA of the lane's 4 states x 2 rows
 };
 
-template <typename T, int TC, int NW, bool HAS_Z, bool REV>
-__device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, const Task& t, BwdSmem<TC, HAS_Z>& sm) {
+template <typename T, bool HAS_Z, bool REV>
+__device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, const Task& t, long long task, BwdWarpSmem& sm,
+                                               int lane) {
     const b200_sscan_fwd_params& p = q.f;
-    constexpr int TP = BwdSmem<TC, HAS_Z>::TP;
-    constexpr int SP = BwdSmem<TC, HAS_Z>::SP;
-    constexpr int NTHR = NW * 32;
-    constexpr int EP = (32 * (TC / 4) + NTHR - 1) / NTHR;  // passes of the (4 steps per thread) epilogue
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, w = tid >> 5;
+    constexpr bool ASYNC = sizeof(T) == 4;
+    const int sq = lane >> 3, i = lane & 7;
     const int L = p.seqlen, N = p.dstate;
-    const bool row_ok = lane < t.nrows;
-    const int d_lane = t.d0 + lane;
+    const int c0 = 2 * sq;
+    const bool okA = i < t.nrows, okB = i + 8 < t.nrows;
+    const int dA_ = t.d0 + i, dB_ = t.d0 + i + 8;
 
-    float2 An[2], A2[2], h[2], dA[2];
+    float2 h[SPT];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int n = w * SPW + 2 * j;
-        An[j].x = (row_ok && n < N) ? __ldg(p.A + (size_t)d_lane * N + n) : 0.f;
-        An[j].y = (row_ok && n + 1 < N) ? __ldg(p.A + (size_t)d_lane * N + n + 1) : 0.f;
-        A2[j] = make_float2(An[j].x * kLog2e, An[j].y * kLog2e);
+    for (int j = 0; j < SPT; ++j) {
+        const int n = sq * SPT + j;
+        float2 a2;
+        a2.x = (okA && n < N) ? __ldg(p.A + (size_t)dA_ * N + n) * kLog2e : 0.f;
+        a2.y = (okB && n < N) ? __ldg(p.A + (size_t)dB_ * N + n) * kLog2e : 0.f;
+        sm.A2[j][lane] = a2;   // private to this lane: no synchronisation needed
+        sm.dA[j][lane] = make_float2(0.f, 0.f);
         h[j] = make_float2(0.f, 0.f);
-        dA[j] = make_float2(0.f, 0.f);
     }
-    if (tid < 32) {
-        sm.D[tid] = (p.D && row_ok) ? __ldg(p.D + d_lane) : 0.f;
-        sm.bias[tid] = (p.delta_bias && row_ok) ? __ldg(p.delta_bias + d_lane) : 0.f;
-    }
+    const float biasA = (p.delta_bias && okA) ? __ldg(p.delta_bias + dA_) : 0.f;
+    const float biasB = (p.delta_bias && okB) ? __ldg(p.delta_bias + dB_) : 0.f;
+    const float DA = (p.D && okA) ? __ldg(p.D + dA_) : 0.f;
+    const float DB = (p.D && okB) ? __ldg(p.D + dB_) : 0.f;
     const bool softplus = p.delta_softplus != 0;
-    float dD_acc[EP], dbias_acc[EP];  // this thread's share of the per-row sums (its rows are fixed across chunks)
-#pragma unroll
-    for (int k = 0; k < EP; ++k) { dD_acc[k] = 0.f; dbias_acc[k] = 0.f; }
+    float dD_A = 0.f, dD_B = 0.f, dbias_A = 0.f, dbias_B = 0.f;  // this lane's share (its two columns of every chunk)
 
     const T* u_base = (const T*)p.u + (size_t)t.b * p.u_batch_stride + (size_t)(t.g / p.u_group_div) * p.u_group_stride +
                       (size_t)t.r0 * p.u_row_stride;
@@ -431,32 +495,43 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     const bool vec_u = can_vectorize<T>(p.u, p.u_row_stride, p.u_batch_stride, p.u_group_stride, L);
     const bool vec_d = can_vectorize<T>(p.delta, p.delta_row_stride, p.delta_batch_stride, 0, L);
     const bool vec_g = can_vectorize<T>(q.dout, q.dout_row_stride, q.dout_batch_stride, q.dout_group_stride, L);
-    const bool vec_z = HAS_Z && can_vectorize<T>(p.z, p.z_row_stride, p.z_batch_stride, 0, L);
-    const bool vec_out = !HAS_Z && can_vectorize<T>(q.du, q.du_row_stride, q.du_batch_stride, 0, L) &&
-                         can_vectorize<T>(q.ddelta, q.ddelta_row_stride, q.ddelta_batch_stride, 0, L);
+    const bool vec_B = can_vectorize<T>(p.B, p.B_state_stride, p.B_batch_stride, p.B_group_stride, L);
+    const bool vec_C = can_vectorize<T>(p.C, p.C_state_stride, p.C_batch_stride, p.C_group_stride, L);
+    const bool vec_du = pair_vec_ok<T>(q.du, q.du_row_stride, q.du_batch_stride, L);
+    const bool vec_dd = pair_vec_ok<T>(q.ddelta, q.ddelta_row_stride, q.ddelta_batch_stride, L);
+    const bool vec_dz = HAS_Z && pair_vec_ok<T>(q.dz, q.dz_row_stride, q.dz_batch_stride, L);
 
     const int nck = (L + TC - 1) / TC;
-    const float* ck = p.ckpt + (size_t)blockIdx.x * (size_t)(nck - 1) * NS * 32;
-    const int item = rs_item<TC>(lane);
+    const float* ck = p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR;
 
+    const bool fast = vec_u && vec_d && vec_g && vec_B && vec_C;
+    const Stager su = make_row_stager(sm.raw[0][0], (const float*)u_base, p.u_row_stride, t.nrows, lane);
+    const Stager sd = make_row_stager(sm.raw[0][1], (const float*)d_base, p.delta_row_stride, t.nrows, lane);
+    const Stager sg = make_row_stager(sm.raw[0][2], (const float*)g_base, q.dout_row_stride, t.nrows, lane);
+    const Stager sB = make_bc_stager(sm.bc[0][0], (const float*)B_base, p.B_state_stride, N, lane);
+    const Stager sC = make_bc_stager(sm.bc[0][1], (const float*)C_base, p.C_state_stride, N, lane);
+    const int lc = (lane & 1) * 4;
     auto l_lo_of = [&](int c) { return REV ? L - (c + 1) * TC : c * TC; };
     auto prefetch = [&](int c) {  // chunk c (scan order); chunks are visited last -> first
         if (c >= 0) {
             const int buf = c & 1, l_lo = l_lo_of(c);
-            stage_rows<T, TC, NTHR>(sm.u[buf], u_base, p.u_row_stride, t.nrows, l_lo, L, vec_u, tid);
-            stage_rows<T, TC, NTHR>(sm.d[buf], d_base, p.delta_row_stride, t.nrows, l_lo, L, vec_d, tid);
-            stage_rows<T, TC, NTHR>(sm.g[buf], g_base, q.dout_row_stride, t.nrows, l_lo, L, vec_g, tid);
-            if (HAS_Z) stage_rows<T, TC, NTHR>(sm.z[buf], z_base, p.z_row_stride, t.nrows, l_lo, L, vec_z, tid);
-            stage_bc<T, TC, NTHR>(sm.B[buf], B_base, p.B_state_stride, N, l_lo, L, tid);
-            stage_bc<T, TC, NTHR>(sm.C[buf], C_base, p.C_state_stride, N, l_lo, L, tid);
-            if (c > 0) {  // entry state of the chunk: 2 KB contiguous
-                const float* src = ck + (size_t)(c - 1) * NS * 32;
-#pragma unroll
-                for (int idx0 = 0; idx0 < NS * 32 / 4; idx0 += NTHR) cp_async16(&sm.ck[buf][(idx0 + tid) * 4], src + (idx0 + tid) * 4, true);
-            } else {
-#pragma unroll
-                for (int idx0 = 0; idx0 < NS * 32; idx0 += NTHR) sm.ck[buf][idx0 + tid] = 0.f;
+            if (ASYNC) {
+                if (fast) {
+                    const int l = l_lo + lc;
+                    stage16(su, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    stage16(sd, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    stage16(sg, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    stage16(sB, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
+                    stage16(sC, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
+                } else {
+                    stage_rows_slow(sm.raw[buf][0], (const float*)u_base, p.u_row_stride, t.nrows, l_lo, L, lane);
+                    stage_rows_slow(sm.raw[buf][1], (const float*)d_base, p.delta_row_stride, t.nrows, l_lo, L, lane);
+                    stage_rows_slow(sm.raw[buf][2], (const float*)g_base, q.dout_row_stride, t.nrows, l_lo, L, lane);
+                    stage_bc_slow(sm.bc[buf][0], (const float*)B_base, p.B_state_stride, N, l_lo, L, lane);
+                    stage_bc_slow(sm.bc[buf][1], (const float*)C_base, p.C_state_stride, N, l_lo, L, lane);
+                }
             }
+            if (c > 0) stage_ckpt(sm.ck[buf], ck + (size_t)(c - 1) * NS * TR, lane);
         }
         cp_async_commit();
     };
@@ -465,245 +540,235 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
 
     for (int c = nck - 1; c >= 0; --c) {
         const int buf = c & 1;
-        const int s0 = c * TC;
-        const int nv = min(TC, L - s0);
         const int l_lo = l_lo_of(c);
+        const int la = l_lo + c0;
+        const bool v0 = la >= 0 && la < L, v1 = la + 1 >= 0 && la + 1 < L;
         cp_async_wait<1>();
-        __syncthreads();  // (1)
-        // ---- pre-pass (once per element): delta', its sigmoid, the gated upstream gradient ----
+        __syncwarp();
+        float uA[2], uB[2], dlA[2], dlB[2], gA[2], gB[2];
+        if (ASYNC) {
+            const float2 ua = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i, c0)]);
+            const float2 ub = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i + 8, c0)]);
+            const float2 da = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i, c0)]);
+            const float2 db = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i + 8, c0)]);
+            const float2 ga = *reinterpret_cast<const float2*>(&sm.raw[buf][2][raw_pos(i, c0)]);
+            const float2 gb = *reinterpret_cast<const float2*>(&sm.raw[buf][2][raw_pos(i + 8, c0)]);
+            uA[0] = ua.x; uA[1] = ua.y; uB[0] = ub.x; uB[1] = ub.y;
+            dlA[0] = da.x; dlA[1] = da.y; dlB[0] = db.x; dlB[1] = db.y;
+            gA[0] = ga.x; gA[1] = ga.y; gB[0] = gb.x; gB[1] = gb.y;
+        } else {
+            fill_bc_sync<T>(sm.bc[buf][0], B_base, p.B_state_stride, N, l_lo, L, lane);
+            fill_bc_sync<T>(sm.bc[buf][1], C_base, p.C_state_stride, N, l_lo, L, lane);
 #pragma unroll
-        for (int idx0 = 0; idx0 < 32 * (TC / 4); idx0 += NTHR) {
-            const int idx = idx0 + tid;
-            if ((32 * (TC / 4)) % NTHR != 0 && idx >= 32 * (TC / 4)) break;  // warp-uniform (TC/4*32 is a multiple of 32)
-            const int rr = idx / (TC / 4), cq = (idx % (TC / 4)) * 4;
-            const int o = rr * TP + cq;
-            const float4 dr = *reinterpret_cast<const float4*>(&sm.d[buf][o]);
-            const float bias = sm.bias[rr];
-            const float draw[4] = {dr.x, dr.y, dr.z, dr.w};
-            float dl[4], sg[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int l = l_lo + cq + k;
-                float v = draw[k] + bias, sgv = 1.f;
-                if (softplus) {
-                    const SoftplusSig r = softplus_sigmoid(v);
-                    v = r.sp;
-                    sgv = r.sig;
-                }
-                if (l < 0 || l >= L) { v = 0.f; sgv = 0.f; }  // identity steps (u and dout are already zero-filled)
-                dl[k] = v;
-                sg[k] = sgv;
+            for (int e = 0; e < 2; ++e) {
+                const bool v = e ? v1 : v0;
+                uA[e] = (okA && v) ? ldg_stream(u_base + (size_t)i * p.u_row_stride + la + e) : 0.f;
+                uB[e] = (okB && v) ? ldg_stream(u_base + (size_t)(i + 8) * p.u_row_stride + la + e) : 0.f;
+                dlA[e] = (okA && v) ? ldg_stream(d_base + (size_t)i * p.delta_row_stride + la + e) : 0.f;
+                dlB[e] = (okB && v) ? ldg_stream(d_base + (size_t)(i + 8) * p.delta_row_stride + la + e) : 0.f;
+                gA[e] = (okA && v) ? ldg_stream(g_base + (size_t)i * q.dout_row_stride + la + e) : 0.f;
+                gB[e] = (okB && v) ? ldg_stream(g_base + (size_t)(i + 8) * q.dout_row_stride + la + e) : 0.f;
             }
-            *reinterpret_cast<float4*>(&sm.d[buf][o]) = make_float4(dl[0], dl[1], dl[2], dl[3]);
-            *reinterpret_cast<float4*>(&sm.sg[o]) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+        }
+        // ---- prologue (once per element): delta', its sigmoid, the gated upstream gradient ----
+        float sgA[2], sgB[2], dzA[2], dzB[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const bool v = e ? v1 : v0;
+            float a = dlA[e] + biasA, b = dlB[e] + biasB, sa = 1.f, sb = 1.f;
+            if (softplus) {
+                const SoftplusSig ra = softplus_sigmoid(a), rb = softplus_sigmoid(b);
+                a = ra.sp; sa = ra.sig; b = rb.sp; sb = rb.sig;
+            }
+            const bool va = okA && v, vb = okB && v;
+            dlA[e] = va ? a : 0.f; sgA[e] = va ? sa : 0.f;  // identity steps (u and dout are already zero there)
+            dlB[e] = vb ? b : 0.f; sgB[e] = vb ? sb : 0.f;
             if (HAS_Z) {
-                const float4 zr = *reinterpret_cast<const float4*>(&sm.z[buf][o]);
-                const float4 gr = *reinterpret_cast<const float4*>(&sm.g[buf][o]);
-                const float zz[4] = {zr.x, zr.y, zr.z, zr.w};
-                const float go[4] = {gr.x, gr.y, gr.z, gr.w};
-                float dzc[4], gg[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float s = sigmoidf_(zz[k]);
-                    dzc[k] = go[k] * s * (1.f + zz[k] * (1.f - s));  // dout * d silu(z)/dz
-                    gg[k] = go[k] * zz[k] * s;                       // dout * silu(z)
-                }
-                *reinterpret_cast<float4*>(&sm.z[buf][o]) = make_float4(dzc[0], dzc[1], dzc[2], dzc[3]);
-                *reinterpret_cast<float4*>(&sm.g[buf][o]) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+                const float za = va ? ldg_stream(z_base + (size_t)i * p.z_row_stride + la + e) : 0.f;
+                const float zb = vb ? ldg_stream(z_base + (size_t)(i + 8) * p.z_row_stride + la + e) : 0.f;
+                const float s_a = sigmoidf_(za), s_b = sigmoidf_(zb);
+                dzA[e] = gA[e] * s_a * (1.f + za * (1.f - s_a));  // dout * d silu(z)/dz
+                dzB[e] = gB[e] * s_b * (1.f + zb * (1.f - s_b));
+                gA[e] *= za * s_a;                                 // dout * silu(z)
+                gB[e] *= zb * s_b;
             }
+            *reinterpret_cast<float2*>(&sm.ex[0][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e], dlB[e]);
+            *reinterpret_cast<float2*>(&sm.ex[1][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e] * uA[e], dlB[e] * uB[e]);
+            *reinterpret_cast<float2*>(&sm.ex[2][(c0 + e) * EXS + 2 * i]) = make_float2(gA[e], gB[e]);
         }
-        __syncthreads();  // (2)
-
-        // ---- this lane's row of the chunk in registers, in scan order ----
-        float dl[TC], duu[TC], go[TC];
-        float2 s1[TC], s2[TC];
-        float2 yacc[HAS_Z ? TC : 1];
-#pragma unroll
-        for (int i4 = 0; i4 < TC / 4; ++i4) {
-            const int cb = REV ? TC - 4 - 4 * i4 : 4 * i4;
-            const float4 u4 = ld4<REV>(&sm.u[buf][lane * TP + cb]);
-            const float4 d4 = ld4<REV>(&sm.d[buf][lane * TP + cb]);
-            const float4 g4 = ld4<REV>(&sm.g[buf][lane * TP + cb]);
-            dl[i4 * 4] = d4.x; dl[i4 * 4 + 1] = d4.y; dl[i4 * 4 + 2] = d4.z; dl[i4 * 4 + 3] = d4.w;
-            go[i4 * 4] = g4.x; go[i4 * 4 + 1] = g4.y; go[i4 * 4 + 2] = g4.z; go[i4 * 4 + 3] = g4.w;
-            duu[i4 * 4] = d4.x * u4.x; duu[i4 * 4 + 1] = d4.y * u4.y; duu[i4 * 4 + 2] = d4.z * u4.z; duu[i4 * 4 + 3] = d4.w * u4.w;
+        // park what the epilogue needs where only this lane looks (its own slots of the raw tiles)
+        if (!ASYNC) {
+            *reinterpret_cast<float2*>(&sm.raw[buf][0][raw_pos(i, c0)]) = make_float2(uA[0], uA[1]);
+            *reinterpret_cast<float2*>(&sm.raw[buf][0][raw_pos(i + 8, c0)]) = make_float2(uB[0], uB[1]);
         }
+        *reinterpret_cast<float2*>(&sm.raw[buf][1][raw_pos(i, c0)]) = make_float2(sgA[0], sgA[1]);
+        *reinterpret_cast<float2*>(&sm.raw[buf][1][raw_pos(i + 8, c0)]) = make_float2(sgB[0], sgB[1]);
+        if (HAS_Z) {
+            *reinterpret_cast<float2*>(&sm.raw[buf][2][raw_pos(i, c0)]) = make_float2(dzA[0], dzA[1]);
+            *reinterpret_cast<float2*>(&sm.raw[buf][2][raw_pos(i + 8, c0)]) = make_float2(dzB[0], dzB[1]);
+        }
+        __syncwarp();
+        float2 dl2[TC], q2[TC], go2[TC], s1[TC], s2[TC], yacc[HAS_Z ? TC : 1];
 #pragma unroll
-        for (int i = 0; i < TC; ++i) {
-            s1[i] = make_float2(0.f, 0.f);
-            s2[i] = make_float2(0.f, 0.f);
-            if (HAS_Z) yacc[i] = make_float2(0.f, 0.f);
+        for (int cc = 0; cc < TC; ++cc) {
+            dl2[cc] = *reinterpret_cast<const float2*>(&sm.ex[0][cc * EXS + 2 * i]);
+            q2[cc] = *reinterpret_cast<const float2*>(&sm.ex[1][cc * EXS + 2 * i]);
+            go2[cc] = *reinterpret_cast<const float2*>(&sm.ex[2][cc * EXS + 2 * i]);
+            s1[cc] = make_float2(0.f, 0.f);
+            s2[cc] = make_float2(0.f, 0.f);
+            if constexpr (HAS_Z) yacc[cc] = make_float2(0.f, 0.f);
         }
 
-        // ---- this warp's states, one packed pair at a time ----
+        // ---- this lane's 4 states, one after the other ----
 #pragma unroll
-        for (int pr = 0; pr < SPW / 2; ++pr) {
-            const int n = w * SPW + 2 * pr;
-            if (n < N) {  // warp-uniform
-                float2 a[TC], ax[TC];
-                float2 xp = make_float2(sm.ck[buf][n * 32 + lane], sm.ck[buf][(n + 1) * 32 + lane]);
-                // forward recompute of the chunk from its checkpoint
+        for (int j = 0; j < SPT; ++j) {
+            const int n = sq * SPT + j;
+            const float2 A2j = sm.A2[j][lane];
+            float2 xm1 = make_float2(0.f, 0.f);
+            if (c > 0) xm1 = *reinterpret_cast<const float2*>(&sm.ck[buf][sq * CKS + j * 16 + 2 * i]);
+            float Bv[TC];
 #pragma unroll
-                for (int i = 0; i < TC; ++i) {
-                    const int cc = REV ? TC - 1 - i : i;
-                    const float2 Bv = *reinterpret_cast<const float2*>(&sm.B[buf][cc * PB + n]);
-                    const float2 e = __fmul2_rn(dup2(dl[i]), A2[pr]);
-                    a[i] = make_float2(ex2(e.x), ex2(e.y));
-                    ax[i] = __fmul2_rn(a[i], xp);
-                    xp = __ffma2_rn(dup2(duu[i]), Bv, ax[i]);
-                }
-                // adjoint recurrence, last step first.  gn = a_{i+1} * (adjoint of x_{i+1})
-                float2 gn = h[pr];
-                float2 dAp = make_float2(0.f, 0.f);
-                float vB0[TC], vB1[TC], vC0[TC], vC1[TC];
+            for (int hh = 0; hh < 2; ++hh) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&sm.bc[buf][0][sq * BCS + j * TC + hh * 4]);
+                Bv[hh * 4] = b4.x; Bv[hh * 4 + 1] = b4.y; Bv[hh * 4 + 2] = b4.z; Bv[hh * 4 + 3] = b4.w;
+            }
+            // forward recompute of the chunk from its checkpoint
+            float2 a[TC], x[TC];
+            {
+                float2 xs = xm1;
 #pragma unroll
-                for (int i = TC - 1; i >= 0; --i) {
-                    const int cc = REV ? TC - 1 - i : i;
-                    const float2 Bv = *reinterpret_cast<const float2*>(&sm.B[buf][cc * PB + n]);
-                    const float2 Cv = *reinterpret_cast<const float2*>(&sm.C[buf][cc * PB + n]);
-                    const float2 go2 = dup2(go[i]), du2 = dup2(duu[i]);
-                    const float2 g = __ffma2_rn(go2, Cv, gn);
-                    const float2 xv = __ffma2_rn(du2, Bv, ax[i]);
-                    const float2 vC = __fmul2_rn(go2, xv);
-                    const float2 vB = __fmul2_rn(g, du2);
-                    vC0[i] = vC.x; vC1[i] = vC.y; vB0[i] = vB.x; vB1[i] = vB.y;
-                    s1[i] = __ffma2_rn(g, Bv, s1[i]);
-                    const float2 wv = __fmul2_rn(g, ax[i]);
-                    s2[i] = __ffma2_rn(An[pr], wv, s2[i]);
-                    dAp = __ffma2_rn(wv, dup2(dl[i]), dAp);
-                    if (HAS_Z) yacc[i] = __ffma2_rn(Cv, xv, yacc[i]);
-                    gn = __fmul2_rn(a[i], g);
-                }
-                h[pr] = gn;
-                dA[pr] = __fadd2_rn(dA[pr], dAp);
-                // dB/dC: sum over the 32 rows of this warp, then one atomic per (state, step)
-                const float rB0 = reduce_scatter<TC>(vB0, lane);
-                const float rC0 = reduce_scatter<TC>(vC0, lane);
-                const float rB1 = reduce_scatter<TC>(vB1, lane);
-                const float rC1 = reduce_scatter<TC>(vC1, lane);
-                if ((lane & 3) == 0 && item < nv) {
-                    const int sl = s0 + item;
-                    const int ll = REV ? (L - 1 - sl) : sl;
-                    atomicAdd(dB_base + (size_t)n * L + ll, rB0);
-                    atomicAdd(dC_base + (size_t)n * L + ll, rC0);
-                    if (n + 1 < N) {
-                        atomicAdd(dB_base + (size_t)(n + 1) * L + ll, rB1);
-                        atomicAdd(dC_base + (size_t)(n + 1) * L + ll, rC1);
-                    }
+                for (int s = 0; s < TC; ++s) {
+                    const int cc = REV ? TC - 1 - s : s;
+                    a[s] = ex2_2(__fmul2_rn(dl2[cc], A2j));
+                    const float2 qB = make_float2(q2[cc].x * Bv[cc], q2[cc].y * Bv[cc]);
+                    xs = __ffma2_rn(a[s], xs, qB);
+                    x[s] = xs;
                 }
             }
-        }
-        // this warp's partial sums over its states, stored in memory-order columns
+            // adjoint recurrence, last step first.  gn = a_{s+1} * (adjoint of x_{s+1})
+            float Cv[TC];
 #pragma unroll
-        for (int i4 = 0; i4 < TC / 4; ++i4) {
-            const int cb = REV ? TC - 4 - 4 * i4 : 4 * i4;
-            const int i = 4 * i4;
-            st4<REV>(&sm.part[w][lane * SP + cb], s1[i].x + s1[i].y, s1[i + 1].x + s1[i + 1].y, s1[i + 2].x + s1[i + 2].y,
-                     s1[i + 3].x + s1[i + 3].y);
-            st4<REV>(&sm.part[w][lane * SP + TC + cb], s2[i].x + s2[i].y, s2[i + 1].x + s2[i + 1].y, s2[i + 2].x + s2[i + 2].y,
-                     s2[i + 3].x + s2[i + 3].y);
-            if (HAS_Z)
-                st4<REV>(&sm.part[w][lane * SP + 2 * TC + cb], yacc[i].x + yacc[i].y, yacc[i + 1].x + yacc[i + 1].y,
-                         yacc[i + 2].x + yacc[i + 2].y, yacc[i + 3].x + yacc[i + 3].y);
+            for (int hh = 0; hh < 2; ++hh) {
+                const float4 c4 = *reinterpret_cast<const float4*>(&sm.bc[buf][1][sq * BCS + j * TC + hh * 4]);
+                Cv[hh * 4] = c4.x; Cv[hh * 4 + 1] = c4.y; Cv[hh * 4 + 2] = c4.z; Cv[hh * 4 + 3] = c4.w;
+            }
+            float2 gn = h[j];
+            float2 dAp = make_float2(0.f, 0.f);
+            float vB[TC], vC[TC];
+#pragma unroll
+            for (int s = TC - 1; s >= 0; --s) {
+                const int cc = REV ? TC - 1 - s : s;
+                const float2 xprev = s > 0 ? x[s - 1] : xm1;
+                float2 g;
+                g.x = fmaf(go2[cc].x, Cv[cc], gn.x);
+                g.y = fmaf(go2[cc].y, Cv[cc], gn.y);
+                vC[cc] = fmaf(go2[cc].y, x[s].y, go2[cc].x * x[s].x);  // sum over the row pair
+                vB[cc] = fmaf(g.y, q2[cc].y, g.x * q2[cc].x);
+                s1[cc].x = fmaf(g.x, Bv[cc], s1[cc].x);
+                s1[cc].y = fmaf(g.y, Bv[cc], s1[cc].y);
+                gn = __fmul2_rn(a[s], g);
+                const float2 wv = __fmul2_rn(gn, xprev);
+                s2[cc] = __ffma2_rn(A2j, wv, s2[cc]);  // A * log2(e): rescaled by ln 2 in the epilogue
+                dAp = __ffma2_rn(wv, dl2[cc], dAp);
+                if constexpr (HAS_Z) {
+                    yacc[cc].x = fmaf(Cv[cc], x[s].x, yacc[cc].x);
+                    yacc[cc].y = fmaf(Cv[cc], x[s].y, yacc[cc].y);
+                }
+            }
+            h[j] = gn;
+            sm.dA[j][lane] = __fadd2_rn(sm.dA[j][lane], dAp);
+            // dB / dC: sum over the 16 rows, lane i ends with column i: one RED per (state, quantity)
+            const float rB = rs8_rows(vB, lane);
+            const float rC = rs8_rows(vC, lane);
+            if (n < N && (unsigned)(l_lo + i) < (unsigned)L) {
+                const int off = n * L + l_lo + i;   // N * L < 2^31 (checked on the host)
+                atomicAdd(dB_base + off, rB);
+                atomicAdd(dC_base + off, rC);
+            }
         }
-        __syncthreads();  // (3)
 
-        // ---- per-element gradients, four steps per thread ----
-#pragma unroll
-        for (int k = 0; k < EP; ++k) {
-            const int idx = tid + k * NTHR;
-            if (idx < 32 * (TC / 4)) {
-                const int rr = idx / (TC / 4), cq = (idx % (TC / 4)) * 4;
-                float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f), v2 = v1, vy = v1;
-#pragma unroll
-                for (int ww = 0; ww < NW; ++ww) {
-                    const float4 a1 = *reinterpret_cast<const float4*>(&sm.part[ww][rr * SP + cq]);
-                    const float4 a2 = *reinterpret_cast<const float4*>(&sm.part[ww][rr * SP + TC + cq]);
-                    v1.x += a1.x; v1.y += a1.y; v1.z += a1.z; v1.w += a1.w;
-                    v2.x += a2.x; v2.y += a2.y; v2.z += a2.z; v2.w += a2.w;
-                    if (HAS_Z) {
-                        const float4 a3 = *reinterpret_cast<const float4*>(&sm.part[ww][rr * SP + 2 * TC + cq]);
-                        vy.x += a3.x; vy.y += a3.y; vy.z += a3.z; vy.w += a3.w;
-                    }
-                }
-                const float4 d4 = *reinterpret_cast<const float4*>(&sm.d[buf][rr * TP + cq]);
-                const float4 u4 = *reinterpret_cast<const float4*>(&sm.u[buf][rr * TP + cq]);
-                const float4 g4 = *reinterpret_cast<const float4*>(&sm.g[buf][rr * TP + cq]);
-                const float4 s4 = *reinterpret_cast<const float4*>(&sm.sg[rr * TP + cq]);
-                const float Dv = sm.D[rr];
-                const float s1v[4] = {v1.x, v1.y, v1.z, v1.w}, s2v[4] = {v2.x, v2.y, v2.z, v2.w};
-                const float dlv[4] = {d4.x, d4.y, d4.z, d4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
-                const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, sgv[4] = {s4.x, s4.y, s4.z, s4.w};
-                float du[4], dd[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    du[e] = fmaf(dlv[e], s1v[e], Dv * gv[e]);
-                    // chain rule through softplus: sg = sigmoid(delta + bias) (1 without softplus, 0 off-range)
-                    dd[e] = fmaf(uv[e], s1v[e], s2v[e]) * sgv[e];
-                    dbias_acc[k] += dd[e];                  // off-range / padded rows contribute exact zeros
-                    dD_acc[k] = fmaf(gv[e], uv[e], dD_acc[k]);
-                }
-                if (rr < t.nrows) {
-                    const int l = l_lo + cq;
-                    if (vec_out) {
-                        if (l >= 0 && l < L) {
-                            __stcs(reinterpret_cast<float4*>((float*)du_base + (size_t)rr * q.du_row_stride + l),
-                                   make_float4(du[0], du[1], du[2], du[3]));
-                            __stcs(reinterpret_cast<float4*>((float*)dd_base + (size_t)rr * q.ddelta_row_stride + l),
-                                   make_float4(dd[0], dd[1], dd[2], dd[3]));
-                        }
-                    } else {
-                        const float4 z4 = HAS_Z ? *reinterpret_cast<const float4*>(&sm.z[buf][rr * TP + cq]) : make_float4(0, 0, 0, 0);
-                        const float dzc[4] = {z4.x, z4.y, z4.z, z4.w}, yv[4] = {vy.x, vy.y, vy.z, vy.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (l + e >= 0 && l + e < L) {
-                                stg_stream(du_base + (size_t)rr * q.du_row_stride + l + e, du[e]);
-                                stg_stream(dd_base + (size_t)rr * q.ddelta_row_stride + l + e, dd[e]);
-                                if (HAS_Z) stg_stream(dz_base + (size_t)rr * q.dz_row_stride + l + e, dzc[e] * fmaf(Dv, uv[e], yv[e]));
-                            }
-                        }
-                    }
-                }
+        // ---- per-element gradients: sums over the 16 states, then this lane's 2 rows x 2 columns ----
+        float2 t1a, t1b, t2a, t2b, tya = make_float2(0.f, 0.f), tyb = tya;
+        reduce_states(sm.rd[0], s1, lane, t1a, t1b);
+        reduce_states(sm.rd[1], s2, lane, t2a, t2b);
+        if constexpr (HAS_Z) {
+            __syncwarp();
+            reduce_states(sm.rd[0], yacc, lane, tya, tyb);
+        }
+        {
+            const float2 ua = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i, c0)]);
+            const float2 ub = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i + 8, c0)]);
+            const float2 sa = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i, c0)]);
+            const float2 sb = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i + 8, c0)]);
+            const float2 dl0 = *reinterpret_cast<const float2*>(&sm.ex[0][c0 * EXS + 2 * i]);        // (row A, row B) of column c0
+            const float2 dl1 = *reinterpret_cast<const float2*>(&sm.ex[0][(c0 + 1) * EXS + 2 * i]);
+            const float2 go0 = *reinterpret_cast<const float2*>(&sm.ex[2][c0 * EXS + 2 * i]);
+            const float2 go1 = *reinterpret_cast<const float2*>(&sm.ex[2][(c0 + 1) * EXS + 2 * i]);
+            const float duA0 = fmaf(dl0.x, t1a.x, DA * go0.x), duA1 = fmaf(dl1.x, t1b.x, DA * go1.x);
+            const float duB0 = fmaf(dl0.y, t1a.y, DB * go0.y), duB1 = fmaf(dl1.y, t1b.y, DB * go1.y);
+            // chain rule through softplus: sg = sigmoid(delta + bias) (1 without softplus, 0 off-range)
+            const float ddA0 = fmaf(ua.x, t1a.x, t2a.x * kLn2) * sa.x, ddA1 = fmaf(ua.y, t1b.x, t2b.x * kLn2) * sa.y;
+            const float ddB0 = fmaf(ub.x, t1a.y, t2a.y * kLn2) * sb.x, ddB1 = fmaf(ub.y, t1b.y, t2b.y * kLn2) * sb.y;
+            dbias_A += ddA0 + ddA1;
+            dbias_B += ddB0 + ddB1;
+            dD_A = fmaf(go0.x, ua.x, fmaf(go1.x, ua.y, dD_A));
+            dD_B = fmaf(go0.y, ub.x, fmaf(go1.y, ub.y, dD_B));
+            store_pair<T>(du_base + (size_t)i * q.du_row_stride + la, duA0, duA1, okA && v0, okA && v1, vec_du);
+            store_pair<T>(du_base + (size_t)(i + 8) * q.du_row_stride + la, duB0, duB1, okB && v0, okB && v1, vec_du);
+            store_pair<T>(dd_base + (size_t)i * q.ddelta_row_stride + la, ddA0, ddA1, okA && v0, okA && v1, vec_dd);
+            store_pair<T>(dd_base + (size_t)(i + 8) * q.ddelta_row_stride + la, ddB0, ddB1, okB && v0, okB && v1, vec_dd);
+            if (HAS_Z) {
+                const float2 za = *reinterpret_cast<const float2*>(&sm.raw[buf][2][raw_pos(i, c0)]);
+                const float2 zb = *reinterpret_cast<const float2*>(&sm.raw[buf][2][raw_pos(i + 8, c0)]);
+                store_pair<T>(dz_base + (size_t)i * q.dz_row_stride + la, za.x * fmaf(DA, ua.x, tya.x), za.y * fmaf(DA, ua.y, tyb.x),
+                              okA && v0, okA && v1, vec_dz);
+                store_pair<T>(dz_base + (size_t)(i + 8) * q.dz_row_stride + la, zb.x * fmaf(DB, ub.x, tya.y),
+                              zb.y * fmaf(DB, ub.y, tyb.y), okB && v0, okB && v1, vec_dz);
             }
         }
-        __syncthreads();  // (4) every thread is done with the raw tiles of this chunk
+        __syncwarp();  // every lane is done with this chunk's tiles
         prefetch(c - 2);
     }
     cp_async_wait<0>();
 
-    if (row_ok) {
-        const float dAs[4] = {dA[0].x, dA[0].y, dA[1].x, dA[1].y};
 #pragma unroll
-        for (int j = 0; j < SPW; ++j)
-            if (w * SPW + j < N) atomicAdd(q.dA + (size_t)d_lane * N + w * SPW + j, dAs[j]);
-    }
-    // per-row sums: TC/4 consecutive threads share a row in every epilogue pass
-#pragma unroll
-    for (int k = 0; k < EP; ++k) {
-        const int idx = tid + k * NTHR;
-        float sb = dbias_acc[k], sd = dD_acc[k];
-#pragma unroll
-        for (int m = TC / 8; m >= 1; m >>= 1) {
-            sb += __shfl_xor_sync(0xffffffffu, sb, m);
-            sd += __shfl_xor_sync(0xffffffffu, sd, m);
+    for (int j = 0; j < SPT; ++j) {
+        const int n = sq * SPT + j;
+        if (n < N) {
+            const float2 v = sm.dA[j][lane];
+            if (okA) atomicAdd(q.dA + (size_t)dA_ * N + n, v.x);
+            if (okB) atomicAdd(q.dA + (size_t)dB_ * N + n, v.y);
         }
-        if (idx < 32 * (TC / 4) && (idx % (TC / 4)) == 0) {
-            const int rr = idx / (TC / 4);
-            if (rr < t.nrows) {
-                if (q.ddelta_bias) atomicAdd(q.ddelta_bias + t.d0 + rr, sb);
-                if (q.dD) atomicAdd(q.dD + t.d0 + rr, sd);
-            }
+    }
+    // per-row sums: the four state-quad lanes of a row pair each hold two columns' worth
+#pragma unroll
+    for (int m = 8; m <= 16; m <<= 1) {
+        dD_A += __shfl_xor_sync(0xffffffffu, dD_A, m);
+        dD_B += __shfl_xor_sync(0xffffffffu, dD_B, m);
+        dbias_A += __shfl_xor_sync(0xffffffffu, dbias_A, m);
+        dbias_B += __shfl_xor_sync(0xffffffffu, dbias_B, m);
+    }
+    if (sq == 0) {
+        if (okA) {
+            if (q.ddelta_bias) atomicAdd(q.ddelta_bias + dA_, dbias_A);
+            if (q.dD) atomicAdd(q.dD + dA_, dD_A);
+        }
+        if (okB) {
+            if (q.ddelta_bias) atomicAdd(q.ddelta_bias + dB_, dbias_B);
+            if (q.dD) atomicAdd(q.dD + dB_, dD_B);
         }
     }
 }
 
-template <typename T, int TC, int NW, bool HAS_Z>
-__global__ void __launch_bounds__(NW * 32, NW == 4 ? 3 : 4) sscan_bwd_kernel(const __grid_constant__ b200_sscan_bwd_params q) {
-    __shared__ __align__(16) BwdSmem<TC, HAS_Z> sm;
-    const Task t = decode_task(q.f, blockIdx.x);
-    if (t.rev) sscan_bwd_body<T, TC, NW, HAS_Z, true>(q, t, sm);
-    else sscan_bwd_body<T, TC, NW, HAS_Z, false>(q, t, sm);
+template <typename T, bool HAS_Z>
+__global__ void __maxnreg__(184) sscan_bwd_kernel(const __grid_constant__ b200_sscan_bwd_params q, long long n_tasks) {
+    __shared__ __align__(16) BwdWarpSmem sm;
+    const int lane = threadIdx.x;
+    const long long task = blockIdx.x;
+    (void)n_tasks;
+    const Task t = decode_task(q.f, task);
+    if (t.rev) sscan_bwd_body<T, HAS_Z, true>(q, t, task, sm, lane);
+    else sscan_bwd_body<T, HAS_Z, false>(q, t, task, sm, lane);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -721,46 +786,34 @@ static int validate(const b200_sscan_fwd_params* p) {
     B200_REQUIRE(p->io_dtype >= B200_F32 && p->io_dtype <= B200_F16, "b200_sscan: bad io_dtype %d", p->io_dtype);
     B200_REQUIRE(p->rev_mask == 0 || p->n_groups <= 32, "b200_sscan: rev_mask needs n_groups <= 32");
     B200_REQUIRE(p->u_group_div >= 1, "b200_sscan: u_group_div must be >= 1");
+    B200_REQUIRE((long long)p->dstate * p->seqlen < (1ll << 31), "b200_sscan: dstate * seqlen must be < 2^31");
     B200_REQUIRE(p->u && p->delta && p->A && p->B && p->C, "b200_sscan: u/delta/A/B/C must be non-NULL");
-    B200_REQUIRE(p->ckpt == nullptr || p->ckpt_every == 8, "b200_sscan: ckpt_every must be 8");
+    B200_REQUIRE(p->ckpt == nullptr || p->ckpt_every == TC, "b200_sscan: ckpt_every must be %d", TC);
+    B200_REQUIRE((reinterpret_cast<uintptr_t>(p->ckpt) & 15) == 0, "b200_sscan: ckpt must be 16-byte aligned");
     return 0;
 }
 
 static long long n_tasks(const b200_sscan_fwd_params* p) {
     const int rpg = p->dim / p->n_groups;
-    return (long long)p->batch * p->n_groups * ((rpg + 31) / 32);
+    return (long long)p->batch * p->n_groups * tiles_per_group(rpg);
 }
 
-template <typename T, bool HAS_Z>
-static int launch_fwd_z(const b200_sscan_fwd_params* p, cudaStream_t st) {
-    const unsigned grid = (unsigned)n_tasks(p);
-    switch ((p->dstate + SPW - 1) / SPW) {
-        case 1: sscan_fwd_kernel<T, 16, 1, HAS_Z><<<grid, 32, 0, st>>>(*p); break;
-        case 2: sscan_fwd_kernel<T, 16, 2, HAS_Z><<<grid, 64, 0, st>>>(*p); break;
-        case 3: sscan_fwd_kernel<T, 16, 3, HAS_Z><<<grid, 96, 0, st>>>(*p); break;
-        default: sscan_fwd_kernel<T, 16, 4, HAS_Z><<<grid, 128, 0, st>>>(*p); break;
-    }
-    return check_launch("sscan_fwd_kernel");
-}
 template <typename T>
 static int launch_fwd(const b200_sscan_fwd_params* p, cudaStream_t st) {
-    return p->z ? launch_fwd_z<T, true>(p, st) : launch_fwd_z<T, false>(p, st);
+    const long long nt = n_tasks(p);
+    const unsigned grid = (unsigned)((nt + WPB - 1) / WPB);
+    if (p->z) sscan_fwd_kernel<T, true><<<grid, WPB * 32, 0, st>>>(*p, nt);
+    else sscan_fwd_kernel<T, false><<<grid, WPB * 32, 0, st>>>(*p, nt);
+    return check_launch("sscan_fwd_kernel");
 }
 
-template <typename T, bool HAS_Z>
-static int launch_bwd_z(const b200_sscan_bwd_params* q, cudaStream_t st) {
-    const unsigned grid = (unsigned)n_tasks(&q->f);
-    switch ((q->f.dstate + SPW - 1) / SPW) {
-        case 1: sscan_bwd_kernel<T, 8, 1, HAS_Z><<<grid, 32, 0, st>>>(*q); break;
-        case 2: sscan_bwd_kernel<T, 8, 2, HAS_Z><<<grid, 64, 0, st>>>(*q); break;
-        case 3: sscan_bwd_kernel<T, 8, 3, HAS_Z><<<grid, 96, 0, st>>>(*q); break;
-        default: sscan_bwd_kernel<T, 8, 4, HAS_Z><<<grid, 128, 0, st>>>(*q); break;
-    }
-    return check_launch("sscan_bwd_kernel");
-}
 template <typename T>
 static int launch_bwd(const b200_sscan_bwd_params* q, cudaStream_t st) {
-    return q->f.z ? launch_bwd_z<T, true>(q, st) : launch_bwd_z<T, false>(q, st);
+    const long long nt = n_tasks(&q->f);
+    const unsigned grid = (unsigned)((nt + WPB - 1) / WPB);
+    if (q->f.z) sscan_bwd_kernel<T, true><<<grid, WPB * 32, 0, st>>>(*q, nt);
+    else sscan_bwd_kernel<T, false><<<grid, WPB * 32, 0, st>>>(*q, nt);
+    return check_launch("sscan_bwd_kernel");
 }
 
 }  // namespace b200
@@ -772,9 +825,9 @@ extern "C" size_t b200_sscan_ckpt_bytes(int32_t batch, int32_t dim, int32_t seql
     (void)dstate;
     if (batch <= 0 || dim <= 0 || seqlen <= 0 || n_groups <= 0 || dim % n_groups || ckpt_every <= 0) return 0;
     const int rpg = dim / n_groups;
-    const size_t tasks = (size_t)batch * n_groups * ((rpg + 31) / 32);
+    const size_t tasks = (size_t)batch * n_groups * tiles_per_group(rpg);
     const size_t nck = (seqlen + ckpt_every - 1) / ckpt_every;
-    const size_t bytes = tasks * (nck - 1) * NS * 32 * sizeof(float);
+    const size_t bytes = tasks * (nck - 1) * NS * TR * sizeof(float);
     return bytes ? bytes : 16;
 }
 
@@ -794,7 +847,6 @@ extern "C" int b200_sscan_bwd(const b200_sscan_bwd_params* q, b200_stream_t stre
     B200_REQUIRE(q != nullptr, "b200_sscan_bwd: params is NULL");
     if (int rc = validate(&q->f)) return rc;
     B200_REQUIRE(q->f.ckpt != nullptr, "b200_sscan_bwd: the forward checkpoints (f.ckpt) are required");
-    B200_REQUIRE((reinterpret_cast<uintptr_t>(q->f.ckpt) & 15) == 0, "b200_sscan_bwd: ckpt must be 16-byte aligned");
     B200_REQUIRE(q->dout && q->du && q->ddelta && q->dA && q->dB && q->dC, "b200_sscan_bwd: dout/du/ddelta/dA/dB/dC must be non-NULL");
     B200_REQUIRE((q->f.z == nullptr) == (q->dz == nullptr), "b200_sscan_bwd: dz must be given exactly when z is");
     B200_REQUIRE(q->dout_group_div >= 1, "b200_sscan_bwd: dout_group_div must be >= 1");
