@@ -445,9 +445,10 @@ struct BwdWarpSmem {
     float bc[2][2][4 * BCS];    // [stage][B, C]
     float ck[2][4 * CKS];       // state entering the chunk
     float ex[3][TC * EXS];      // delta' | delta' * u | gated dout, [column][row pair][2]
-    float rd[2][4 * RDS];       // reductions over the state quads
+    float rd[4 * RDS];          // reduction over the state quads
     float2 A2[SPT][32];         // per-lane constants / accumulators that would not fit in registers:
-    float2 dA[SPT][32];         // A * log2(e) and the running dA of the lane's 4 states x 2 rows
+    float2 dA[SPT][32];         // A * log2(e), the running dA and the adjoint carry of the lane's 4 states x 2 rows
+    float2 h[SPT][32];
 };
 
 template <typename T, bool HAS_Z, bool REV>
@@ -461,7 +462,6 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     const bool okA = i < t.nrows, okB = i + 8 < t.nrows;
     const int dA_ = t.d0 + i, dB_ = t.d0 + i + 8;
 
-    float2 h[SPT];
 #pragma unroll
     for (int j = 0; j < SPT; ++j) {
         const int n = sq * SPT + j;
@@ -470,7 +470,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
         a2.y = (okB && n < N) ? __ldg(p.A + (size_t)dB_ * N + n) * kLog2e : 0.f;
         sm.A2[j][lane] = a2;   // private to this lane: no synchronisation needed
         sm.dA[j][lane] = make_float2(0.f, 0.f);
-        h[j] = make_float2(0.f, 0.f);
+        sm.h[j][lane] = make_float2(0.f, 0.f);
     }
     const float biasA = (p.delta_bias && okA) ? __ldg(p.delta_bias + dA_) : 0.f;
     const float biasB = (p.delta_bias && okB) ? __ldg(p.delta_bias + dB_) : 0.f;
@@ -652,7 +652,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
                 const float4 c4 = *reinterpret_cast<const float4*>(&sm.bc[buf][1][sq * BCS + j * TC + hh * 4]);
                 Cv[hh * 4] = c4.x; Cv[hh * 4 + 1] = c4.y; Cv[hh * 4 + 2] = c4.z; Cv[hh * 4 + 3] = c4.w;
             }
-            float2 gn = h[j];
+            float2 gn = sm.h[j][lane];
             float2 dAp = make_float2(0.f, 0.f);
             float vB[TC], vC[TC];
 #pragma unroll
@@ -675,10 +675,10 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
                     yacc[cc].y = fmaf(Cv[cc], x[s].y, yacc[cc].y);
                 }
             }
-            h[j] = gn;
+            sm.h[j][lane] = gn;
             sm.dA[j][lane] = __fadd2_rn(sm.dA[j][lane], dAp);
             // dB / dC: sum over the 16 rows, lane i ends with column i: one RED per (state, quantity)
-            const float rB = rs8_rows(vB, lane);
+            const float rB = rs8_rows(vB, lane);   // (a shared-memory transposition was measured slower: LSU wavefronts)
             const float rC = rs8_rows(vC, lane);
             if (n < N && (unsigned)(l_lo + i) < (unsigned)L) {
                 const int off = n * L + l_lo + i;   // N * L < 2^31 (checked on the host)
@@ -689,11 +689,12 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
 
         // ---- per-element gradients: sums over the 16 states, then this lane's 2 rows x 2 columns ----
         float2 t1a, t1b, t2a, t2b, tya = make_float2(0.f, 0.f), tyb = tya;
-        reduce_states(sm.rd[0], s1, lane, t1a, t1b);
-        reduce_states(sm.rd[1], s2, lane, t2a, t2b);
+        reduce_states(sm.rd, s1, lane, t1a, t1b);
+        __syncwarp();
+        reduce_states(sm.rd, s2, lane, t2a, t2b);
         if constexpr (HAS_Z) {
             __syncwarp();
-            reduce_states(sm.rd[0], yacc, lane, tya, tyb);
+            reduce_states(sm.rd, yacc, lane, tya, tyb);
         }
         {
             const float2 ua = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i, c0)]);
@@ -761,7 +762,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
 }
 
 template <typename T, bool HAS_Z>
-__global__ void __maxnreg__(184) sscan_bwd_kernel(const __grid_constant__ b200_sscan_bwd_params q, long long n_tasks) {
+__global__ void __launch_bounds__(WPB * 32, 12) sscan_bwd_kernel(const __grid_constant__ b200_sscan_bwd_params q, long long n_tasks) {
     __shared__ __align__(16) BwdWarpSmem sm;
     const int lane = threadIdx.x;
     const long long task = blockIdx.x;
@@ -798,6 +799,11 @@ static long long n_tasks(const b200_sscan_fwd_params* p) {
     return (long long)p->batch * p->n_groups * tiles_per_group(rpg);
 }
 
+// static shared memory only, but 12-16 resident warp-CTAs need the large carve-out
+template <typename K> static void prefer_smem(K kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 template <typename T>
 static int launch_fwd(const b200_sscan_fwd_params* p, cudaStream_t st) {
     const long long nt = n_tasks(p);
@@ -809,6 +815,8 @@ static int launch_fwd(const b200_sscan_fwd_params* p, cudaStream_t st) {
 
 template <typename T>
 static int launch_bwd(const b200_sscan_bwd_params* q, cudaStream_t st) {
+    static const bool once = (prefer_smem(sscan_bwd_kernel<T, true>), prefer_smem(sscan_bwd_kernel<T, false>), true);
+    (void)once;
     const long long nt = n_tasks(&q->f);
     const unsigned grid = (unsigned)((nt + WPB - 1) / WPB);
     if (q->f.z) sscan_bwd_kernel<T, true><<<grid, WPB * 32, 0, st>>>(*q, nt);
