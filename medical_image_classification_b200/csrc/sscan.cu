@@ -21,8 +21,8 @@
 //     with the total of step i: one fully used fp32 RED per (state, chunk, quantity);
 //   * a group can be scanned in reverse time (rev_mask) and groups can share u / dout rows (u_group_div,
 //     dout_group_div): that is all the SS2D cross-scan / cross-merge needs (MedMamba.py:393-395, 420-424),
-//     the flipped copies never exist.  Register arrays are indexed by MEMORY column, the scan direction is a
-//     compile-time index map;
+//     the flipped copies never exist.  Register arrays and the exchange tiles are indexed by SCAN step; the
+//     direction only changes (warp-uniform, run-time) shared-memory addresses, so there is one code body;
 //   * backward = recompute: the forward stores the 16-float state entering every 8-step chunk, the backward
 //     walks chunks last -> first, re-derives the states of one chunk in registers and runs the adjoint
 //     recurrence on them.
@@ -223,23 +223,33 @@ __device__ __forceinline__ float rs8_rows(const float (&v)[8], int lane) {
     return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+// One state's 8 steps of B or C in SCAN order (v[s] <-> memory column rev ? 7 - s : s).  The branch is warp-uniform.
+__device__ __forceinline__ void load8_steps(const float* p, bool rev, float (&v)[TC]) {
+    if (!rev) {
+        const float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int s = 0; s < TC; ++s) v[s] = p[TC - 1 - s];
+    }
+}
+
 // Sum 8 per-lane row-pair values over the 4 state quads (lane bits 3-4) through a 2.3 KB shared-memory tile: the
-// lane ends with the totals of columns 2 sq and 2 sq + 1 -- the two columns whose elements it owns in the
-// prologue / epilogue.  8 STS.64 + 8 LDS.64 + 6 packed adds (a shuffle reduce-scatter costs ~100 issue slots).
+// lane ends with the totals of the two scan steps s0, s1 that correspond to the two memory columns (2 sq, 2 sq + 1)
+// whose elements it owns in the prologue / epilogue.  8 STS.64 + 8 LDS.64 + 6 packed adds (a shuffle reduce-scatter costs ~100 issue slots).
 // The tile layout [quad][column][row pair] is padded (RDS) and XOR-skewed so both phases are conflict free.
 __device__ __forceinline__ int rd_pos(int quad, int cc, int i) { return quad * RDS + ((cc * 16 + 2 * i) ^ (((cc >> 1) & 1) << 4)); }
-__device__ __forceinline__ void reduce_states(float* tile, const float2 (&v)[8], int lane, float2& r0, float2& r1) {
+__device__ __forceinline__ void reduce_states(float* tile, const float2 (&v)[8], int lane, int s0, int s1, float2& r0, float2& r1) {
     const int sq = lane >> 3, i = lane & 7;
 #pragma unroll
-    for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<float2*>(tile + rd_pos(sq, cc, i)) = v[cc];
+    for (int s = 0; s < 8; ++s) *reinterpret_cast<float2*>(tile + rd_pos(sq, s, i)) = v[s];
     __syncwarp();
-    const int c0 = 2 * sq;
-    r0 = *reinterpret_cast<const float2*>(tile + rd_pos(0, c0, i));
-    r1 = *reinterpret_cast<const float2*>(tile + rd_pos(0, c0 + 1, i));
+    r0 = *reinterpret_cast<const float2*>(tile + rd_pos(0, s0, i));   // s0 / s1: the scan steps of this lane's two columns
+    r1 = *reinterpret_cast<const float2*>(tile + rd_pos(0, s1, i));
 #pragma unroll
     for (int qd = 1; qd < 4; ++qd) {
-        r0 = __fadd2_rn(r0, *reinterpret_cast<const float2*>(tile + rd_pos(qd, c0, i)));
-        r1 = __fadd2_rn(r1, *reinterpret_cast<const float2*>(tile + rd_pos(qd, c0 + 1, i)));
+        r0 = __fadd2_rn(r0, *reinterpret_cast<const float2*>(tile + rd_pos(qd, s0, i)));
+        r1 = __fadd2_rn(r1, *reinterpret_cast<const float2*>(tile + rd_pos(qd, s1, i)));
     }
 }
 
@@ -253,7 +263,7 @@ struct FwdWarpSmem {
     float rd[4 * RDS];             // reduction over the state quads
 };
 
-template <typename T, bool HAS_Z, bool REV>
+template <typename T, bool HAS_Z>
 __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, const Task& t, long long task, FwdWarpSmem& sm,
                                                int lane) {
     constexpr bool ASYNC = sizeof(T) == 4;
@@ -293,7 +303,9 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
     const int nck = (L + TC - 1) / TC;
     float* ck = p.ckpt ? p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR : nullptr;
 
-    auto l_lo_of = [&](int c) { return REV ? L - (c + 1) * TC : c * TC; };
+    const bool rev = t.rev;
+    const int st0 = rev ? TC - 1 - c0 : c0, st1 = rev ? TC - 2 - c0 : c0 + 1;  // scan steps of this lane's two columns
+    auto l_lo_of = [&](int c) { return rev ? L - (c + 1) * TC : c * TC; };
     const bool fast = vec_u && vec_d && vec_B && vec_C;
     const Stager su = make_row_stager(sm.raw[0][0], (const float*)u_base, p.u_row_stride, t.nrows, lane);
     const Stager sd = make_row_stager(sm.raw[0][1], (const float*)d_base, p.delta_row_stride, t.nrows, lane);
@@ -320,10 +332,12 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
             cp_async_commit();  // (possibly empty) group: keeps the wait_group arithmetic uniform
         }
     };
-    prefetch(0);
-    prefetch(1);
-
-    for (int c = 0; c < nck; ++c) {
+    // software pipeline with ONE prefetch call site (code size): iterations -2 and -1 only prefetch
+    for (int c = -2; c < nck; ++c) {
+        if (c < 0) {
+            prefetch(c + 2);
+            continue;
+        }
         const int buf = c & 1;
         const int l_lo = l_lo_of(c);
         const int la = l_lo + c0;  // sequence position of this lane's first column
@@ -358,11 +372,12 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
             if (softplus) { a = softplus_sigmoid(a).sp; b = softplus_sigmoid(b).sp; }
             dlA[e] = (okA && v) ? a : 0.f;  // out-of-range steps / rows become the identity: decay 1, input 0
             dlB[e] = (okB && v) ? b : 0.f;
-            *reinterpret_cast<float2*>(&sm.ex[0][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e], dlB[e]);
-            *reinterpret_cast<float2*>(&sm.ex[1][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e] * uA[e], dlB[e] * uB[e]);
+            const int st = e ? st1 : st0;   // the exchange tile is indexed by scan step
+            *reinterpret_cast<float2*>(&sm.ex[0][st * EXS + 2 * i]) = make_float2(dlA[e], dlB[e]);
+            *reinterpret_cast<float2*>(&sm.ex[1][st * EXS + 2 * i]) = make_float2(dlA[e] * uA[e], dlB[e] * uB[e]);
         }
         __syncwarp();
-        float2 dl2[TC], q2[TC], y2[TC];
+        float2 dl2[TC], q2[TC], y2[TC];   // indexed by scan step
 #pragma unroll
         for (int cc = 0; cc < TC; ++cc) {
             dl2[cc] = *reinterpret_cast<const float2*>(&sm.ex[0][cc * EXS + 2 * i]);
@@ -375,17 +390,12 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
             const int n = sq * SPT + j;
             if (ck != nullptr && c > 0) *reinterpret_cast<float2*>(ck + (size_t)(c - 1) * NS * TR + n * TR + 2 * i) = x[j];
             float Bv[TC], Cv[TC];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const float4 b4 = *reinterpret_cast<const float4*>(&sm.bc[buf][0][sq * BCS + j * TC + hh * 4]);
-                const float4 c4 = *reinterpret_cast<const float4*>(&sm.bc[buf][1][sq * BCS + j * TC + hh * 4]);
-                Bv[hh * 4] = b4.x; Bv[hh * 4 + 1] = b4.y; Bv[hh * 4 + 2] = b4.z; Bv[hh * 4 + 3] = b4.w;
-                Cv[hh * 4] = c4.x; Cv[hh * 4 + 1] = c4.y; Cv[hh * 4 + 2] = c4.z; Cv[hh * 4 + 3] = c4.w;
-            }
+            load8_steps(&sm.bc[buf][0][sq * BCS + j * TC], rev, Bv);
+            load8_steps(&sm.bc[buf][1][sq * BCS + j * TC], rev, Cv);
             float2 xs = x[j];
 #pragma unroll
             for (int s = 0; s < TC; ++s) {
-                const int cc = REV ? TC - 1 - s : s;
+                const int cc = s;
                 const float2 a = ex2_2(__fmul2_rn(dl2[cc], A2[j]));
                 const float2 qB = make_float2(q2[cc].x * Bv[cc], q2[cc].y * Bv[cc]);
                 xs = __ffma2_rn(a, xs, qB);
@@ -396,7 +406,7 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
         }
         // ---- out = sum over states (4 lanes) + D u (* silu(z)), written at its memory position ----
         float2 r0, r1;
-        reduce_states(sm.rd, y2, lane, r0, r1);
+        reduce_states(sm.rd, y2, lane, st0, st1, r0, r1);
         float oA[2] = {fmaf(DA, uA[0], r0.x), fmaf(DA, uA[1], r1.x)};
         float oB[2] = {fmaf(DB, uB[0], r0.y), fmaf(DB, uB[1], r1.y)};
         if (HAS_Z) {
@@ -433,8 +443,7 @@ __global__ void __launch_bounds__(WPB * 32, 16) sscan_fwd_kernel(const __grid_co
     const long long task = blockIdx.x;
     (void)n_tasks;
     const Task t = decode_task(p, task);
-    if (t.rev) sscan_fwd_body<T, HAS_Z, true>(p, t, task, sm, lane);
-    else sscan_fwd_body<T, HAS_Z, false>(p, t, task, sm, lane);
+    sscan_fwd_body<T, HAS_Z>(p, t, task, sm, lane);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -451,7 +460,7 @@ struct BwdWarpSmem {
     float2 h[SPT][32];
 };
 
-template <typename T, bool HAS_Z, bool REV>
+template <typename T, bool HAS_Z>
 __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, const Task& t, long long task, BwdWarpSmem& sm,
                                                int lane) {
     const b200_sscan_fwd_params& p = q.f;
@@ -511,7 +520,9 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     const Stager sB = make_bc_stager(sm.bc[0][0], (const float*)B_base, p.B_state_stride, N, lane);
     const Stager sC = make_bc_stager(sm.bc[0][1], (const float*)C_base, p.C_state_stride, N, lane);
     const int lc = (lane & 1) * 4;
-    auto l_lo_of = [&](int c) { return REV ? L - (c + 1) * TC : c * TC; };
+    const bool rev = t.rev;
+    const int st0 = rev ? TC - 1 - c0 : c0, st1 = rev ? TC - 2 - c0 : c0 + 1;  // scan steps of this lane's two columns
+    auto l_lo_of = [&](int c) { return rev ? L - (c + 1) * TC : c * TC; };
     auto prefetch = [&](int c) {  // chunk c (scan order); chunks are visited last -> first
         if (c >= 0) {
             const int buf = c & 1, l_lo = l_lo_of(c);
@@ -535,10 +546,12 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
         }
         cp_async_commit();
     };
-    prefetch(nck - 1);
-    prefetch(nck - 2);
-
-    for (int c = nck - 1; c >= 0; --c) {
+    // software pipeline with ONE prefetch call site (code size): iterations nck+1 and nck only prefetch
+    for (int c = nck + 1; c >= 0; --c) {
+        if (c >= nck) {
+            prefetch(c - 2);
+            continue;
+        }
         const int buf = c & 1;
         const int l_lo = l_lo_of(c);
         const int la = l_lo + c0;
@@ -592,9 +605,10 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
                 gA[e] *= za * s_a;                                 // dout * silu(z)
                 gB[e] *= zb * s_b;
             }
-            *reinterpret_cast<float2*>(&sm.ex[0][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e], dlB[e]);
-            *reinterpret_cast<float2*>(&sm.ex[1][(c0 + e) * EXS + 2 * i]) = make_float2(dlA[e] * uA[e], dlB[e] * uB[e]);
-            *reinterpret_cast<float2*>(&sm.ex[2][(c0 + e) * EXS + 2 * i]) = make_float2(gA[e], gB[e]);
+            const int st = e ? st1 : st0;   // the exchange tile is indexed by scan step
+            *reinterpret_cast<float2*>(&sm.ex[0][st * EXS + 2 * i]) = make_float2(dlA[e], dlB[e]);
+            *reinterpret_cast<float2*>(&sm.ex[1][st * EXS + 2 * i]) = make_float2(dlA[e] * uA[e], dlB[e] * uB[e]);
+            *reinterpret_cast<float2*>(&sm.ex[2][st * EXS + 2 * i]) = make_float2(gA[e], gB[e]);
         }
         // park what the epilogue needs where only this lane looks (its own slots of the raw tiles)
         if (!ASYNC) {
@@ -619,7 +633,9 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
             if constexpr (HAS_Z) yacc[cc] = make_float2(0.f, 0.f);
         }
 
-        // ---- this lane's 4 states, one after the other ----
+        // ---- this lane's 4 states, one after the other.  The scan direction is a RUNTIME property (tiles indexed by
+        //      scan step): with one compile-time body per direction the two unrolled copies evicted each other from the
+        //      32 KB instruction cache whenever an SM ran both kinds of task (measured: +25 % time under SS2D's rev_mask) ----
 #pragma unroll
         for (int j = 0; j < SPT; ++j) {
             const int n = sq * SPT + j;
@@ -627,18 +643,14 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
             float2 xm1 = make_float2(0.f, 0.f);
             if (c > 0) xm1 = *reinterpret_cast<const float2*>(&sm.ck[buf][sq * CKS + j * 16 + 2 * i]);
             float Bv[TC];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const float4 b4 = *reinterpret_cast<const float4*>(&sm.bc[buf][0][sq * BCS + j * TC + hh * 4]);
-                Bv[hh * 4] = b4.x; Bv[hh * 4 + 1] = b4.y; Bv[hh * 4 + 2] = b4.z; Bv[hh * 4 + 3] = b4.w;
-            }
+            load8_steps(&sm.bc[buf][0][sq * BCS + j * TC], rev, Bv);
             // forward recompute of the chunk from its checkpoint
             float2 a[TC], x[TC];
             {
                 float2 xs = xm1;
 #pragma unroll
                 for (int s = 0; s < TC; ++s) {
-                    const int cc = REV ? TC - 1 - s : s;
+                    const int cc = s;
                     a[s] = ex2_2(__fmul2_rn(dl2[cc], A2j));
                     const float2 qB = make_float2(q2[cc].x * Bv[cc], q2[cc].y * Bv[cc]);
                     xs = __ffma2_rn(a[s], xs, qB);
@@ -647,17 +659,13 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
             }
             // adjoint recurrence, last step first.  gn = a_{s+1} * (adjoint of x_{s+1})
             float Cv[TC];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const float4 c4 = *reinterpret_cast<const float4*>(&sm.bc[buf][1][sq * BCS + j * TC + hh * 4]);
-                Cv[hh * 4] = c4.x; Cv[hh * 4 + 1] = c4.y; Cv[hh * 4 + 2] = c4.z; Cv[hh * 4 + 3] = c4.w;
-            }
+            load8_steps(&sm.bc[buf][1][sq * BCS + j * TC], rev, Cv);
             float2 gn = sm.h[j][lane];
             float2 dAp = make_float2(0.f, 0.f);
             float vB[TC], vC[TC];
 #pragma unroll
             for (int s = TC - 1; s >= 0; --s) {
-                const int cc = REV ? TC - 1 - s : s;
+                const int cc = s;
                 const float2 xprev = s > 0 ? x[s - 1] : xm1;
                 float2 g;
                 g.x = fmaf(go2[cc].x, Cv[cc], gn.x);
@@ -680,8 +688,9 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
             // dB / dC: sum over the 16 rows, lane i ends with column i: one RED per (state, quantity)
             const float rB = rs8_rows(vB, lane);   // (a shared-memory transposition was measured slower: LSU wavefronts)
             const float rC = rs8_rows(vC, lane);
-            if (n < N && (unsigned)(l_lo + i) < (unsigned)L) {
-                const int off = n * L + l_lo + i;   // N * L < 2^31 (checked on the host)
+            const int lcol = l_lo + (rev ? TC - 1 - i : i);   // lane i holds scan step i
+            if (n < N && (unsigned)lcol < (unsigned)L) {
+                const int off = n * L + lcol;   // N * L < 2^31 (checked on the host)
                 atomicAdd(dB_base + off, rB);
                 atomicAdd(dC_base + off, rC);
             }
@@ -689,22 +698,22 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
 
         // ---- per-element gradients: sums over the 16 states, then this lane's 2 rows x 2 columns ----
         float2 t1a, t1b, t2a, t2b, tya = make_float2(0.f, 0.f), tyb = tya;
-        reduce_states(sm.rd, s1, lane, t1a, t1b);
+        reduce_states(sm.rd, s1, lane, st0, st1, t1a, t1b);
         __syncwarp();
-        reduce_states(sm.rd, s2, lane, t2a, t2b);
+        reduce_states(sm.rd, s2, lane, st0, st1, t2a, t2b);
         if constexpr (HAS_Z) {
             __syncwarp();
-            reduce_states(sm.rd, yacc, lane, tya, tyb);
+            reduce_states(sm.rd, yacc, lane, st0, st1, tya, tyb);
         }
         {
             const float2 ua = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i, c0)]);
             const float2 ub = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i + 8, c0)]);
             const float2 sa = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i, c0)]);
             const float2 sb = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i + 8, c0)]);
-            const float2 dl0 = *reinterpret_cast<const float2*>(&sm.ex[0][c0 * EXS + 2 * i]);        // (row A, row B) of column c0
-            const float2 dl1 = *reinterpret_cast<const float2*>(&sm.ex[0][(c0 + 1) * EXS + 2 * i]);
-            const float2 go0 = *reinterpret_cast<const float2*>(&sm.ex[2][c0 * EXS + 2 * i]);
-            const float2 go1 = *reinterpret_cast<const float2*>(&sm.ex[2][(c0 + 1) * EXS + 2 * i]);
+            const float2 dl0 = *reinterpret_cast<const float2*>(&sm.ex[0][st0 * EXS + 2 * i]);        // (row A, row B) of column c0
+            const float2 dl1 = *reinterpret_cast<const float2*>(&sm.ex[0][st1 * EXS + 2 * i]);
+            const float2 go0 = *reinterpret_cast<const float2*>(&sm.ex[2][st0 * EXS + 2 * i]);
+            const float2 go1 = *reinterpret_cast<const float2*>(&sm.ex[2][st1 * EXS + 2 * i]);
             const float duA0 = fmaf(dl0.x, t1a.x, DA * go0.x), duA1 = fmaf(dl1.x, t1b.x, DA * go1.x);
             const float duB0 = fmaf(dl0.y, t1a.y, DB * go0.y), duB1 = fmaf(dl1.y, t1b.y, DB * go1.y);
             // chain rule through softplus: sg = sigmoid(delta + bias) (1 without softplus, 0 off-range)
@@ -768,8 +777,7 @@ __global__ void __launch_bounds__(WPB * 32, 12) sscan_bwd_kernel(const __grid_co
     const long long task = blockIdx.x;
     (void)n_tasks;
     const Task t = decode_task(q.f, task);
-    if (t.rev) sscan_bwd_body<T, HAS_Z, true>(q, t, task, sm, lane);
-    else sscan_bwd_body<T, HAS_Z, false>(q, t, task, sm, lane);
+    sscan_bwd_body<T, HAS_Z>(q, t, task, sm, lane);
 }
 
 // ----------------------------------------------------------------------------------------------
