@@ -14,8 +14,8 @@
 // 128x64x32 tiles, operands staged global -> registers -> shared with the decay / dt' factors
 // applied on the way in, TF32 mma with the 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32 accumulate)
 // so that fp32 callers get fp32-accurate products (precision = 0), or a single TF32 pass
-// (precision = 1: what the reference's tl.dot does on fp32 inputs).  The dense C B^T and
-// state contractions additionally have a tcgen05 / TMEM path (ssd_tc.cu) selected by precision = 1.
+// (precision = 1: what the reference's tl.dot does on fp32 inputs).  These are warp-level mma.sync tiles
+// (HMMA in SASS), not yet tcgen05 / TMEM: DESIGN.md lists that as the next step for this operator.
 // The backward is the exact adjoint of the chunked forward; it re-uses the forward's dt', cs,
 // chunk-entry states and C B^T (workspace) and the forward output (for the "stable" d cs term).
 #include "common.cuh"

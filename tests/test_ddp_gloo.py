@@ -1,0 +1,71 @@
+"""N > 1 host logic on CPU: one process per rank, batch sharded across ranks, no data-path
+collective, DDP all-reduce(avg) of the parameter gradients -- world_size 2, gloo backend.  The scan runs through
+oracle/cpu_path.py here (there is no GPU in this container); the sharding / reduction logic is what is tested:
+the rank-averaged gradients must equal the single-process gradients of the full batch."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle.cpu_path import bind_cpu_core
+from medical_image_classification_b200.models import VSSM
+
+
+def _net():
+    torch.manual_seed(0)
+    net = VSSM(num_classes=6, depths=[1, 1, 1, 1], dims=[8, 16, 32, 64], drop_path_rate=0.0)
+    bind_cpu_core(net)
+    net.eval()   # BatchNorm on running statistics: per-rank batch statistics (no SyncBN, as in ddp_train.py) would differ by design
+    return net
+
+
+def _data():
+    g = torch.Generator().manual_seed(1)
+    return torch.randn(4, 3, 32, 32, generator=g), torch.randint(0, 6, (4,), generator=g)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = _net()
+    ddp = torch.nn.parallel.DistributedDataParallel(net)
+    x, y = _data()
+    per = x.shape[0] // world
+    xs, ys = x[rank * per:(rank + 1) * per], y[rank * per:(rank + 1) * per]   # DistributedSampler-style shard
+    loss = torch.nn.functional.cross_entropy(ddp(xs), ys)
+    loss.backward()
+    t = torch.tensor([float(loss)])
+    dist.all_reduce(t)           # the bench's max/mean-over-ranks plumbing
+    if rank == 0:
+        grads = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        torch.save({"grads": grads, "loss_sum": float(t)}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    net = _net()
+    x, y = _data()
+    losses = [torch.nn.functional.cross_entropy(net(x[i:i + 2]), y[i:i + 2]) for i in (0, 2)]
+    (sum(losses) / 2).backward()
+    assert abs(got["loss_sum"] - float(sum(losses))) < 1e-5
+    n = 0
+    for k, p in net.named_parameters():
+        if p.grad is None:
+            continue
+        ref = p.grad.numpy()
+        err = np.abs(got["grads"][k].numpy() - ref).max() / max(np.abs(ref).max(), 1e-12)
+        assert err < 1e-4, (k, err)
+        n += 1
+    assert n > 20
