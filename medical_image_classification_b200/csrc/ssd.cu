@@ -407,7 +407,39 @@ __global__ void __launch_bounds__(NTHR, 2) chunk_state_kernel(View4<T> X, View4<
 }
 
 // ---- K3: state passing over chunks (in place: local states -> chunk-entry states) --------------
-__global__ void state_pass_kernel(Dims d, Ws ws, const float* init, float* fin) {
+// HBM-bound streaming pass: 128-bit accesses, 32-bit indexing, and the loads of 8 chunks are issued before the
+// (sequential) recurrence over them so each thread keeps 8 independent 16-byte requests in flight.
+constexpr int SPB = 8;  // chunks per batch of loads
+__global__ void __launch_bounds__(256) state_pass_kernel(Dims d, Ws ws, const float* init, float* fin) {
+    const int PN4 = d.P * d.N / 4;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= PN4) return;
+    const int h = blockIdx.y % d.H, b = blockIdx.y / d.H;
+    const size_t cstride = (size_t)d.H * PN4;                                       // float4 units between chunks
+    float4* st = reinterpret_cast<float4*>(ws.states) + ((size_t)b * d.nc * d.H + h) * PN4 + e;
+    const float* csq = ws.cs + ((size_t)b * d.H + h) * d.nc * d.Q + d.Q - 1;
+    float4 run = init ? reinterpret_cast<const float4*>(init)[((size_t)b * d.H + h) * PN4 + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < d.nc; c0 += SPB) {
+        float4 loc[SPB];
+        float dec[SPB];
+#pragma unroll
+        for (int k = 0; k < SPB; ++k)
+            if (c0 + k < d.nc) {
+                loc[k] = st[(size_t)(c0 + k) * cstride];
+                dec[k] = exp_acc(__ldg(csq + (size_t)(c0 + k) * d.Q));
+            }
+#pragma unroll
+        for (int k = 0; k < SPB; ++k)
+            if (c0 + k < d.nc) {
+                st[(size_t)(c0 + k) * cstride] = run;
+                run = make_float4(fmaf(dec[k], run.x, loc[k].x), fmaf(dec[k], run.y, loc[k].y), fmaf(dec[k], run.z, loc[k].z),
+                                  fmaf(dec[k], run.w, loc[k].w));
+            }
+    }
+    if (fin) reinterpret_cast<float4*>(fin)[((size_t)b * d.H + h) * PN4 + e] = run;
+}
+// element-wise fallback (P * N not a multiple of 4)
+__global__ void state_pass_kernel_scalar(Dims d, Ws ws, const float* init, float* fin) {
     const size_t PN = (size_t)d.P * d.N;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)d.batch * d.H * PN) return;
@@ -537,7 +569,66 @@ __global__ void __launch_bounds__(NTHR, 2) chunk_scan_kernel(View4<T> X, View4<T
 
 // ---- B2: reverse state passing: dstates[c] (off-diagonal adjoint) -> G[c] = adjoint of Sin[c+1];
 //          dcsQ[b][h][c] = <G[c], Sin[c+1]>  (accumulated with atomics; caller zero-fills) ----------
+// Same streaming structure as K3 (128-bit, 8 chunks of loads in flight); the per-chunk dot products are kept in
+// registers and block-reduced once per batch of chunks.
 __global__ void __launch_bounds__(NTHR) state_pass_bwd_kernel(Dims d, Ws ws, float* dstates, float* dcsQ) {
+    __shared__ float red[NTHR / 32][SPB];
+    const int PN4 = d.P * d.N / 4;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = e < PN4;
+    const int h = blockIdx.y % d.H, b = blockIdx.y / d.H;
+    const size_t cstride = (size_t)d.H * PN4;
+    float4* ds = reinterpret_cast<float4*>(dstates) + ((size_t)b * d.nc * d.H + h) * PN4 + (ok ? e : 0);
+    const float4* sn = reinterpret_cast<const float4*>(ws.states) + ((size_t)b * d.nc * d.H + h) * PN4 + (ok ? e : 0);
+    const float* csq = ws.cs + ((size_t)b * d.H + h) * d.nc * d.Q + d.Q - 1;
+    float* dq = dcsQ + ((size_t)b * d.H + h) * d.nc;
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = d.nc - 1; c0 >= 0; c0 -= SPB) {   // chunks c0, c0-1, ...
+        float4 off[SPB], nxt[SPB];
+        float dec[SPB], dot[SPB];
+#pragma unroll
+        for (int k = 0; k < SPB; ++k) {
+            const int c = c0 - k;
+            off[k] = z4; nxt[k] = z4; dec[k] = 0.f;
+            if (c >= 0) {
+                if (ok) off[k] = ds[(size_t)c * cstride];
+                if (ok && c + 1 < d.nc) nxt[k] = sn[(size_t)(c + 1) * cstride];
+                dec[k] = exp_acc(__ldg(csq + (size_t)c * d.Q));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SPB; ++k) {
+            const int c = c0 - k;
+            dot[k] = 0.f;
+            if (c >= 0) {
+                if (ok) ds[(size_t)c * cstride] = run;
+                dot[k] = run.x * nxt[k].x + run.y * nxt[k].y + run.z * nxt[k].z + run.w * nxt[k].w;
+                run = make_float4(fmaf(dec[k], run.x, off[k].x), fmaf(dec[k], run.y, off[k].y), fmaf(dec[k], run.z, off[k].z),
+                                  fmaf(dec[k], run.w, off[k].w));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SPB; ++k) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) dot[k] += __shfl_xor_sync(0xffffffffu, dot[k], o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = dot[k];
+        }
+        __syncthreads();
+        if (threadIdx.x < SPB) {
+            const int c = c0 - (int)threadIdx.x;
+            if (c >= 0 && c + 1 < d.nc) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < NTHR / 32; ++w) t += red[w][threadIdx.x];
+                atomicAdd(dq + c, t);
+            }
+        }
+        __syncthreads();
+    }
+}
+// element-wise fallback (P * N not a multiple of 4)
+__global__ void __launch_bounds__(NTHR) state_pass_bwd_kernel_scalar(Dims d, Ws ws, float* dstates, float* dcsQ) {
     __shared__ float red[NTHR / 32];
     const size_t PN = (size_t)d.P * d.N;
     const int nblk = (int)((PN + NTHR - 1) / NTHR);
@@ -980,8 +1071,17 @@ static int fwd_impl(const b200_ssd_fwd_params* p, cudaStream_t st) {
            p->dt_stride[2], p->A, p->dt_bias, p->dt_softplus, p->dt_min, p->dt_max, d, ws);
     LAUNCH((chunk_state_kernel<T, 0>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, X, Bv, d, ws, ws.states, x3);
     {
-        const size_t n = (size_t)d.batch * d.H * d.P * d.N;
-        LAUNCH(state_pass_kernel, (n + 255) / 256, 256, 0, st, d, ws, p->initial_states, p->final_states);
+        const size_t PN = (size_t)d.P * d.N;
+        const bool vec = PN % 4 == 0 && ((uintptr_t)ws.states & 15) == 0 && ((uintptr_t)p->initial_states & 15) == 0 &&
+                         ((uintptr_t)p->final_states & 15) == 0 && (size_t)d.batch * d.H <= 65535;
+        if (vec) {
+            state_pass_kernel<<<dim3((unsigned)((PN / 4 + 255) / 256), (unsigned)(d.batch * d.H)), 256, 0, st>>>(d, ws, p->initial_states,
+                                                                                                            p->final_states);
+            if (int rc_ = check_launch("state_pass_kernel")) return rc_;
+        } else {
+            const size_t n = (size_t)d.batch * d.H * PN;
+            LAUNCH(state_pass_kernel_scalar, (n + 255) / 256, 256, 0, st, d, ws, p->initial_states, p->final_states);
+        }
     }
     LAUNCH((cb_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, Cv, Bv, d, ws, x3);
     LAUNCH((chunk_scan_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Cv, p->D, d, ws, (T*)p->out,
@@ -1028,8 +1128,17 @@ static int bwd_impl(const b200_ssd_bwd_params* q, cudaStream_t st) {
     }
     LAUNCH((chunk_state_kernel<T, 1>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, DO, Cv, d, ws, sc.dstates, x3);
     {
-        const int nblk = (int)(((size_t)d.P * d.N + NTHR - 1) / NTHR);
-        LAUNCH(state_pass_bwd_kernel, (size_t)d.batch * d.H * nblk, NTHR, 0, st, d, ws, sc.dstates, sc.dcsQ);
+        const size_t PN = (size_t)d.P * d.N;
+        const bool vec = PN % 4 == 0 && ((uintptr_t)ws.states & 15) == 0 && ((uintptr_t)sc.dstates & 15) == 0 &&
+                         (size_t)d.batch * d.H <= 65535;
+        if (vec) {
+            state_pass_bwd_kernel<<<dim3((unsigned)((PN / 4 + NTHR - 1) / NTHR), (unsigned)(d.batch * d.H)), NTHR, 0, st>>>(d, ws, sc.dstates,
+                                                                                                                   sc.dcsQ);
+            if (int rc_ = check_launch("state_pass_bwd_kernel")) return rc_;
+        } else {
+            const int nblk = (int)((PN + NTHR - 1) / NTHR);
+            LAUNCH(state_pass_bwd_kernel_scalar, (size_t)d.batch * d.H * nblk, NTHR, 0, st, d, ws, sc.dstates, sc.dcsQ);
+        }
     }
     LAUNCH((dx_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Bv, DO, OUT, p->D, d, ws, sc.dstates, q->dx,
            sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
