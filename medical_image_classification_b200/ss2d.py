@@ -23,6 +23,50 @@ from .cross import cross_scan_pack, scan_merge
 from .selective_scan_interface import selective_scan_fn
 
 
+class _tf32_matmul:
+    """Context: run fp32 matmuls on the TF32 tensor-core path (restores the global flag on exit)."""
+
+    def __init__(self, on: bool):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        if self.on:
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+class _ProjFn(torch.autograd.Function):
+    """out = W @ X for the x_proj / dt_proj contractions (MedMamba.py:397-400) with the precision fixed at call time
+    for BOTH passes: `tf32=True` is used under autocast, where the reference runs these einsums in bf16 -- TF32 on the
+    fp32 operands keeps more mantissa (10 bits vs 8) and needs no casts; `tf32=False` is exact fp32 (parity tests)."""
+
+    @staticmethod
+    def forward(ctx, W, X, tf32):
+        ctx.save_for_backward(W, X)
+        ctx.tf32 = bool(tf32)
+        with _tf32_matmul(ctx.tf32):
+            return torch.matmul(W, X)
+
+    @staticmethod
+    def backward(ctx, g):
+        W, X = ctx.saved_tensors
+        dW = dX = None
+        with _tf32_matmul(ctx.tf32):
+            if ctx.needs_input_grad[0]:
+                dW = torch.matmul(g, X.transpose(-1, -2))
+                while dW.dim() > W.dim():        # W was broadcast over leading (batch) dimensions
+                    dW = dW.sum(0)
+                for ax, (a, b_) in enumerate(zip(dW.shape, W.shape)):
+                    if a != b_:
+                        dW = dW.sum(ax, keepdim=True)
+            if ctx.needs_input_grad[1]:
+                dX = torch.matmul(W.transpose(-1, -2), g)
+        return dW, dX, None
+
+
 class SS2D(nn.Module):
     def __init__(self, d_model, d_state=16, d_conv=3, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
                  dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, dropout=0.0, conv_bias=True, bias=False,
@@ -95,14 +139,15 @@ class SS2D(nn.Module):
         B, D, H, W = x.shape
         L = H * W
         R, N = self.dt_rank, self.d_state
+        tf32 = torch.is_autocast_enabled()   # the reference computes these projections in bf16 under autocast
         with torch.autocast("cuda", enabled=False):
             x2 = cross_scan_pack(x.float())                         # (B, 2, D, L)
             Wx, Wdt, bias, As, Ds = self._dir_params()
             # directions (0,1) read x2[:,0], (2,3) read x2[:,1]: one GEMM per layout
-            x_dbl = torch.matmul(Wx.reshape(2, 2 * (R + 2 * N), D).unsqueeze(0), x2)   # (B, 2, 2C, L)
+            x_dbl = _ProjFn.apply(Wx.reshape(2, 2 * (R + 2 * N), D).unsqueeze(0), x2, tf32)   # (B, 2, 2C, L)
             x_dbl = x_dbl.view(B, 4, R + 2 * N, L)
             dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-            dts = torch.matmul(Wdt.unsqueeze(0), dts_r)              # (B, 4, D, L)
+            dts = _ProjFn.apply(Wdt.unsqueeze(0), dts_r, tf32)       # (B, 4, D, L)
             y = scan_merge(x2, dts.view(B, 4 * D, L), As, Bs, Cs, Ds, bias, H, W)      # (B, L, D)
         return y.view(B, H, W, D)
 
