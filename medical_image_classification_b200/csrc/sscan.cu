@@ -28,6 +28,10 @@
 //     recurrence on them.
 //
 // Binding pipes: forward = MUFU.EX2 (16 per element) with issue close behind, backward = issue.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
@@ -64,6 +68,41 @@ __device__ __forceinline__ void cp_async16_ca(float* smem, const float* gmem, bo
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier: the u / delta / dout tiles of the aligned fp32 path -------------
+// One 16 x 8 box per tensor and chunk, issued by lane 0, completion counted in bytes on a per-stage mbarrier.
+// SWIZZLE_32B is exactly raw_pos() (16-byte half of a 32-byte row XOR bit 2 of the row index), rows / positions
+// outside the tensor are zero-filled by the copy engine, and none of this traffic touches the LSU wavefront pipe.
+struct RowMaps {
+    CUtensorMap u, delta, dout;   // 4-D: (L, rows per group, groups, batch)
+};
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(float* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// generic-proxy writes / reads of a tile must be ordered before the async proxy (TMA) overwrites it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+constexpr unsigned ROW_TILE_BYTES = TR * TC * sizeof(float);
 
 struct Task {
     int b, g, r0, nrows, rpg, d0;  // d0 = first channel of the task
@@ -261,11 +300,12 @@ struct FwdWarpSmem {
     float bc[2][2][4 * BCS];       // [stage][B, C]
     float ex[2][TC * EXS];         // delta' | delta' * u, [column][row pair][2]
     float rd[4 * RDS];             // reduction over the state quads
+    uint64_t bar[2];               // TMA completion, one per stage
 };
 
-template <typename T, bool HAS_Z>
-__device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, const Task& t, long long task, FwdWarpSmem& sm,
-                                               int lane) {
+template <typename T, bool HAS_Z, bool TMA>
+__device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, const RowMaps& tm, const Task& t,
+                                               long long task, FwdWarpSmem& sm, int lane) {
     constexpr bool ASYNC = sizeof(T) == 4;
     const int sq = lane >> 3, i = lane & 7;
     const int L = p.seqlen, N = p.dstate;
@@ -307,6 +347,7 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
     const int st0 = rev ? TC - 1 - c0 : c0, st1 = rev ? TC - 2 - c0 : c0 + 1;  // scan steps of this lane's two columns
     auto l_lo_of = [&](int c) { return rev ? L - (c + 1) * TC : c * TC; };
     const bool fast = vec_u && vec_d && vec_B && vec_C;
+    constexpr bool tma = TMA;   // host guarantees `fast` whenever it picks the TMA instantiation
     const Stager su = make_row_stager(sm.raw[0][0], (const float*)u_base, p.u_row_stride, t.nrows, lane);
     const Stager sd = make_row_stager(sm.raw[0][1], (const float*)d_base, p.delta_row_stride, t.nrows, lane);
     const Stager sB = make_bc_stager(sm.bc[0][0], (const float*)B_base, p.B_state_stride, N, lane);
@@ -318,8 +359,16 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
                 const int buf = c & 1, l_lo = l_lo_of(c);
                 if (fast) {
                     const int l = l_lo + lc;
-                    stage16(su, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
-                    stage16(sd, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    if (tma) {
+                        if (lane == 0) {
+                            mbar_expect_tx(&sm.bar[buf], 2 * ROW_TILE_BYTES);
+                            tma_load_4d(sm.raw[buf][0], &tm.u, l_lo, t.r0, t.g / p.u_group_div, t.b, &sm.bar[buf]);
+                            tma_load_4d(sm.raw[buf][1], &tm.delta, l_lo, t.r0, t.g, t.b, &sm.bar[buf]);
+                        }
+                    } else {
+                        stage16(su, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                        stage16(sd, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    }
                     stage16(sB, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
                     stage16(sC, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
                 } else {
@@ -332,6 +381,14 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
             cp_async_commit();  // (possibly empty) group: keeps the wait_group arithmetic uniform
         }
     };
+    if (tma) {
+        if (lane == 0) {
+            mbar_init(&sm.bar[0], 1);
+            mbar_init(&sm.bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     // software pipeline with ONE prefetch call site (code size): iterations -2 and -1 only prefetch
     for (int c = -2; c < nck; ++c) {
         if (c < 0) {
@@ -345,6 +402,7 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
         float uA[2], uB[2], dlA[2], dlB[2];
         if (ASYNC) {
             cp_async_wait<1>();
+            if (tma) mbar_wait(&sm.bar[buf], (c >> 1) & 1);   // the (c >> 1)-th use of this stage
             __syncwarp();
             const float2 ua = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i, c0)]);
             const float2 ub = *reinterpret_cast<const float2*>(&sm.raw[buf][0][raw_pos(i + 8, c0)]);
@@ -419,6 +477,7 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
         }
         store_pair<T>(o_base + (size_t)i * p.out_row_stride + la, oA[0], oA[1], okA && v0, okA && v1, vec_o);
         store_pair<T>(o_base + (size_t)(i + 8) * p.out_row_stride + la, oB[0], oB[1], okB && v0, okB && v1, vec_o);
+        if (tma) fence_proxy_async();
         __syncwarp();  // every lane is done with this chunk's tiles
         prefetch(c + 2);
     }
@@ -435,15 +494,14 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
     }
 }
 
-template <typename T, bool HAS_Z>
-__global__ void __launch_bounds__(WPB * 32, 16) sscan_fwd_kernel(const __grid_constant__ b200_sscan_fwd_params p, long long n_tasks) {
-    __shared__ __align__(16) FwdWarpSmem sm;
+template <typename T, bool HAS_Z, bool TMA>
+__global__ void __launch_bounds__(WPB * 32, 16) sscan_fwd_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_constant__ RowMaps tm) {
+    __shared__ __align__(1024) FwdWarpSmem sm;
     static_assert(WPB == 1, "one warp-task per CTA");
     const int lane = threadIdx.x;
     const long long task = blockIdx.x;
-    (void)n_tasks;
     const Task t = decode_task(p, task);
-    sscan_fwd_body<T, HAS_Z>(p, t, task, sm, lane);
+    sscan_fwd_body<T, HAS_Z, TMA>(p, tm, t, task, sm, lane);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -458,11 +516,12 @@ struct BwdWarpSmem {
     float2 A2[SPT][32];         // per-lane constants / accumulators that would not fit in registers:
     float2 dA[SPT][32];         // A * log2(e), the running dA and the adjoint carry of the lane's 4 states x 2 rows
     float2 h[SPT][32];
+    uint64_t bar[2];            // TMA completion, one per stage
 };
 
-template <typename T, bool HAS_Z>
-__device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, const Task& t, long long task, BwdWarpSmem& sm,
-                                               int lane) {
+template <typename T, bool HAS_Z, bool TMA>
+__device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, const RowMaps& tm, const Task& t,
+                                               long long task, BwdWarpSmem& sm, int lane) {
     const b200_sscan_fwd_params& p = q.f;
     constexpr bool ASYNC = sizeof(T) == 4;
     const int sq = lane >> 3, i = lane & 7;
@@ -514,6 +573,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     const float* ck = p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR;
 
     const bool fast = vec_u && vec_d && vec_g && vec_B && vec_C;
+    constexpr bool tma = TMA;   // host guarantees `fast` whenever it picks the TMA instantiation
     const Stager su = make_row_stager(sm.raw[0][0], (const float*)u_base, p.u_row_stride, t.nrows, lane);
     const Stager sd = make_row_stager(sm.raw[0][1], (const float*)d_base, p.delta_row_stride, t.nrows, lane);
     const Stager sg = make_row_stager(sm.raw[0][2], (const float*)g_base, q.dout_row_stride, t.nrows, lane);
@@ -529,9 +589,18 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
             if (ASYNC) {
                 if (fast) {
                     const int l = l_lo + lc;
-                    stage16(su, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
-                    stage16(sd, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
-                    stage16(sg, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    if (tma) {
+                        if (lane == 0) {
+                            mbar_expect_tx(&sm.bar[buf], 3 * ROW_TILE_BYTES);
+                            tma_load_4d(sm.raw[buf][0], &tm.u, l_lo, t.r0, t.g / p.u_group_div, t.b, &sm.bar[buf]);
+                            tma_load_4d(sm.raw[buf][1], &tm.delta, l_lo, t.r0, t.g, t.b, &sm.bar[buf]);
+                            tma_load_4d(sm.raw[buf][2], &tm.dout, l_lo, t.r0, t.g / (int)q.dout_group_div, t.b, &sm.bar[buf]);
+                        }
+                    } else {
+                        stage16(su, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                        stage16(sd, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                        stage16(sg, buf * (unsigned)sizeof(sm.raw[0]), l, L, false);
+                    }
                     stage16(sB, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
                     stage16(sC, buf * (unsigned)sizeof(sm.bc[0]), l, L, true);
                 } else {
@@ -546,6 +615,14 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
         }
         cp_async_commit();
     };
+    if (tma) {
+        if (lane == 0) {
+            mbar_init(&sm.bar[0], 1);
+            mbar_init(&sm.bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     // software pipeline with ONE prefetch call site (code size): iterations nck+1 and nck only prefetch
     for (int c = nck + 1; c >= 0; --c) {
         if (c >= nck) {
@@ -557,6 +634,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
         const int la = l_lo + c0;
         const bool v0 = la >= 0 && la < L, v1 = la + 1 >= 0 && la + 1 < L;
         cp_async_wait<1>();
+        if (ASYNC && tma) mbar_wait(&sm.bar[buf], ((nck - 1 - c) >> 1) & 1);   // the ((nck-1-c) >> 1)-th use of this stage
         __syncwarp();
         float uA[2], uB[2], dlA[2], dlB[2], gA[2], gB[2];
         if (ASYNC) {
@@ -736,6 +814,7 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
                               zb.y * fmaf(DB, ub.y, tyb.y), okB && v0, okB && v1, vec_dz);
             }
         }
+        if (tma) fence_proxy_async();
         __syncwarp();  // every lane is done with this chunk's tiles
         prefetch(c - 2);
     }
@@ -770,14 +849,13 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     }
 }
 
-template <typename T, bool HAS_Z>
-__global__ void __launch_bounds__(WPB * 32, 12) sscan_bwd_kernel(const __grid_constant__ b200_sscan_bwd_params q, long long n_tasks) {
-    __shared__ __align__(16) BwdWarpSmem sm;
+template <typename T, bool HAS_Z, bool TMA>
+__global__ void __launch_bounds__(WPB * 32, 12) sscan_bwd_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_constant__ RowMaps tm) {
+    __shared__ __align__(1024) BwdWarpSmem sm;
     const int lane = threadIdx.x;
     const long long task = blockIdx.x;
-    (void)n_tasks;
     const Task t = decode_task(q.f, task);
-    sscan_bwd_body<T, HAS_Z>(q, t, task, sm, lane);
+    sscan_bwd_body<T, HAS_Z, TMA>(q, tm, t, task, sm, lane);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -812,23 +890,95 @@ template <typename K> static void prefer_smem(K kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+// ---- tensor maps for the TMA row path ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static const EncodeTiledFn fn = [] {
+        const char* on = getenv("B200_SSCAN_TMA");   // opt-in: measured 5 % slower than the LDGSTS staging at 512-byte boxes
+        if (!on || on[0] != '1') return (EncodeTiledFn) nullptr;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        (void)cudaGetLastError();
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+// fp32 activation tensor viewed as (L, rows per group, groups, batch); box = (8 steps, 16 rows, 1, 1), SWIZZLE_32B
+static bool make_row_map(CUtensorMap* m, const void* base, int L, int rpg, int groups, int batch, int64_t row_stride,
+                         int64_t group_stride, int64_t batch_stride) {
+    const EncodeTiledFn enc = encode_tiled();
+    if (!enc || (L & 3) || (reinterpret_cast<uintptr_t>(base) & 15) || (row_stride & 3) || (group_stride & 3) || (batch_stride & 3))
+        return false;
+    if (row_stride <= 0 || group_stride <= 0 || batch_stride <= 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)L, (cuuint64_t)rpg, (cuuint64_t)groups, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)row_stride * 4, (cuuint64_t)group_stride * 4, (cuuint64_t)batch_stride * 4};
+    for (int k = 0; k < 3; ++k)
+        if (strides[k] >= (1ull << 40)) return false;
+    const cuuint32_t box[4] = {TC, TR, 1, 1}, estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool bc_vec_ok(const void* ptr, int64_t state_stride, int64_t batch_stride, int64_t group_stride) {
+    return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (state_stride & 3) == 0 && (batch_stride & 3) == 0 && (group_stride & 3) == 0;
+}
+static bool make_fwd_maps(RowMaps* tm, const b200_sscan_fwd_params* p) {
+    if (p->io_dtype != B200_F32 || encode_tiled() == nullptr) return false;
+    const int rpg = p->dim / p->n_groups;
+    if (p->n_groups % p->u_group_div) return false;
+    // the kernel's TMA instantiation assumes its 16-byte B/C staging is legal too
+    if (!bc_vec_ok(p->B, p->B_state_stride, p->B_batch_stride, p->B_group_stride) ||
+        !bc_vec_ok(p->C, p->C_state_stride, p->C_batch_stride, p->C_group_stride))
+        return false;
+    return make_row_map(&tm->u, p->u, p->seqlen, rpg, p->n_groups / p->u_group_div, p->batch, p->u_row_stride, p->u_group_stride,
+                        p->u_batch_stride) &&
+           make_row_map(&tm->delta, p->delta, p->seqlen, rpg, p->n_groups, p->batch, p->delta_row_stride,
+                        (int64_t)rpg * p->delta_row_stride, p->delta_batch_stride);
+}
+
 template <typename T>
 static int launch_fwd(const b200_sscan_fwd_params* p, cudaStream_t st) {
     const long long nt = n_tasks(p);
     const unsigned grid = (unsigned)((nt + WPB - 1) / WPB);
-    if (p->z) sscan_fwd_kernel<T, true><<<grid, WPB * 32, 0, st>>>(*p, nt);
-    else sscan_fwd_kernel<T, false><<<grid, WPB * 32, 0, st>>>(*p, nt);
+    RowMaps tm;
+    memset(&tm, 0, sizeof(tm));
+    const bool use_tma = sizeof(T) == 4 && make_fwd_maps(&tm, p);
+    if (use_tma) {
+        if (p->z) sscan_fwd_kernel<T, true, sizeof(T) == 4><<<grid, WPB * 32, 0, st>>>(*p, tm);
+        else sscan_fwd_kernel<T, false, sizeof(T) == 4><<<grid, WPB * 32, 0, st>>>(*p, tm);
+    } else {
+        if (p->z) sscan_fwd_kernel<T, true, false><<<grid, WPB * 32, 0, st>>>(*p, tm);
+        else sscan_fwd_kernel<T, false, false><<<grid, WPB * 32, 0, st>>>(*p, tm);
+    }
     return check_launch("sscan_fwd_kernel");
 }
 
 template <typename T>
 static int launch_bwd(const b200_sscan_bwd_params* q, cudaStream_t st) {
-    static const bool once = (prefer_smem(sscan_bwd_kernel<T, true>), prefer_smem(sscan_bwd_kernel<T, false>), true);
+    static const bool once = (prefer_smem(sscan_bwd_kernel<T, true, false>), prefer_smem(sscan_bwd_kernel<T, false, false>),
+                              prefer_smem(sscan_bwd_kernel<T, true, sizeof(T) == 4>), prefer_smem(sscan_bwd_kernel<T, false, sizeof(T) == 4>), true);
     (void)once;
     const long long nt = n_tasks(&q->f);
     const unsigned grid = (unsigned)((nt + WPB - 1) / WPB);
-    if (q->f.z) sscan_bwd_kernel<T, true><<<grid, WPB * 32, 0, st>>>(*q, nt);
-    else sscan_bwd_kernel<T, false><<<grid, WPB * 32, 0, st>>>(*q, nt);
+    RowMaps tm;
+    memset(&tm, 0, sizeof(tm));
+    const int rpg = q->f.dim / q->f.n_groups;
+    const int use_tma = (make_fwd_maps(&tm, &q->f) && q->f.n_groups % (int)q->dout_group_div == 0 &&
+                         make_row_map(&tm.dout, q->dout, q->f.seqlen, rpg, q->f.n_groups / (int)q->dout_group_div, q->f.batch,
+                                      q->dout_row_stride, q->dout_group_stride, q->dout_batch_stride))
+                            ? 1
+                            : 0;
+    if (use_tma && sizeof(T) == 4) {
+        if (q->f.z) sscan_bwd_kernel<T, true, sizeof(T) == 4><<<grid, WPB * 32, 0, st>>>(*q, tm);
+        else sscan_bwd_kernel<T, false, sizeof(T) == 4><<<grid, WPB * 32, 0, st>>>(*q, tm);
+    } else {
+        if (q->f.z) sscan_bwd_kernel<T, true, false><<<grid, WPB * 32, 0, st>>>(*q, tm);
+        else sscan_bwd_kernel<T, false, false><<<grid, WPB * 32, 0, st>>>(*q, tm);
+    }
     return check_launch("sscan_bwd_kernel");
 }
 
