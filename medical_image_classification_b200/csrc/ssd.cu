@@ -18,6 +18,9 @@
 // (HMMA in SASS), not yet tcgen05 / TMEM: DESIGN.md lists that as the next step for this operator.
 // The backward is the exact adjoint of the chunked forward; it re-uses the forward's dt', cs,
 // chunk-entry states and C B^T (workspace) and the forward output (for the "stable" d cs term).
+#include <cstddef>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -302,13 +305,276 @@ __device__ __forceinline__ void gemm_pipeline(Smem& sm, int nkt, LA la, LB lb, S
     }
 }
 
+// ---- engine A: warp-level mma.sync tiles (accumulators in registers) ---------------------------------------
+struct MmaEngine {
+    using Shared = Smem;
+    Acc acc;
+    static __device__ __forceinline__ Shared& smem() {
+        extern __shared__ __align__(1024) unsigned char raw[];
+        return *reinterpret_cast<Shared*>(raw);
+    }
+    template <int TI, bool KI, typename T>
+    static __device__ __forceinline__ void load(RegTile<TI>& r, const T* p, int64_t si, int64_t sk, int ni, int nk, bool vec) {
+        load_raw<TI, KI>(r, p, si, sk, ni, nk, vec);
+    }
+    template <int TI, bool KI, class XF>
+    static __device__ __forceinline__ void store(float* s, const RegTile<TI>& r, XF xf) { store_tile<TI, KI>(s, r, xf); }
+    __device__ __forceinline__ void begin(Shared&) { acc.zero(); }
+    template <bool KIA, bool KIB, class LA, class LB, class SA, class SB>
+    __device__ __forceinline__ void pass(Shared& sm, int nkt, bool x3, LA la, LB lb, SA sa, SB sb) {
+        gemm_pipeline(sm, nkt, la, lb, sa, sb, [&](const float* sA, const float* sB) { warp_mma<KIA, KIB>(acc, sA, sB, x3); });
+    }
+    template <class F> __device__ __forceinline__ void for_each(Shared&, F fn) { for_each_acc(acc, fn); }
+    __device__ __forceinline__ void end(Shared&) {}
+};
+
+// ---- engine B: tcgen05 (UMMA) tiles: operands in the canonical no-swizzle K-major shared-memory layout, fp32
+//      accumulators in tensor memory, one thread issues the MMAs, completion through mbarriers -------------------
+// byte offset of operand element (row i, k) inside a [TI rows x 32 k] tile:
+//     (k / 4) * LBO + (i / 8) * SBO + (i % 8) * 16 + (k % 4) * 4
+// i.e. 8-row x 16-byte core matrices (cute/atom/mma_traits_sm100.hpp, "LayoutType::INTERLEAVE ((8,n),2):((1,SBO),LBO)").
+// SBO and LBO are free descriptor fields: padding them (144 instead of 128, +16) makes both store patterns below
+// bank-conflict free -- a quarter warp storing the eight 16-byte k-chunks of one row, and a warp storing single
+// words of 8 row-quads x 4 consecutive k.  Validated bit-exactly by tools/tc_probe.cu.
+namespace tc {
+constexpr int SBO = 144;
+template <int TI> struct Geo {
+    static constexpr int LBO = (TI / 8) * SBO + 16;
+    static constexpr int BYTES = (BK / 4) * LBO;
+};
+constexpr int A_BYTES = Geo<BM>::BYTES, B_BYTES = Geo<BN>::BYTES;   // 18560, 9344
+constexpr int TMEM_COLS = BN;                                        // 128 lanes x 64 fp32 columns
+
+struct Shared {
+    float cs[2][MAXQ];
+    float dtp[2][MAXQ];
+    float v1[2][MAXQ];
+    float v2[2][MAXQ];
+    float rowf[MAXQ / BK][BM];
+    float red[8];
+    uint64_t bar[2];      // "the MMAs that read operand stage s have completed"
+    uint64_t bar_done;
+    uint32_t tmem_slot, pad_;
+    alignas(128) unsigned char Ahi[2][A_BYTES];
+    alignas(128) unsigned char Bhi[2][B_BYTES];
+    alignas(128) unsigned char Alo[2][A_BYTES];   // low parts of the 3xTF32 split (allocated only in that mode)
+    alignas(128) unsigned char Blo[2][B_BYTES];
+};
+constexpr size_t SMEM_TF32 = offsetof(Shared, Alo), SMEM_X3 = sizeof(Shared);
+
+struct Dst {   // where one operand stage goes
+    unsigned char* hi;
+    unsigned char* lo;
+    bool x3;
+};
+
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(unsigned saddr, unsigned lbo, unsigned sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);   // version 1 (Blackwell), no swizzle, base offset 0
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(
+            s32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}" ::"r"(tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+}  // namespace tc
+
+struct TcEngine {
+    using Shared = tc::Shared;
+    uint32_t tmem;
+    uint32_t issued[2], waited[2];
+    bool started, x3_;
+    static __device__ __forceinline__ Shared& smem() {
+        extern __shared__ __align__(1024) unsigned char raw[];
+        return *reinterpret_cast<Shared*>(raw);
+    }
+    // register-tile mappings (vid = it * 256 + tid).  !KI: as load_raw (k = 4 (vid % 8), i = vid / 8).
+    // KI: a warp covers 8 row-quads x 4 consecutive k:  i = 32 (blk % (TI/32)) + 4 (vid % 8),  k = 4 (blk / (TI/32)) + (vid / 8) % 4
+    template <int TI> static __device__ __forceinline__ void ki_map(int vid, int& i, int& k) {
+        const int blk = vid >> 5;
+        i = 32 * (blk % (TI / 32)) + 4 * (vid & 7);
+        k = 4 * (blk / (TI / 32)) + ((vid >> 3) & 3);
+    }
+    template <int TI, bool KI, typename T>
+    static __device__ __forceinline__ void load(RegTile<TI>& r, const T* p, int64_t si, int64_t sk, int ni, int nk, bool vec) {
+        if constexpr (!KI) {
+            load_raw<TI, false>(r, p, si, sk, ni, nk, vec);
+        } else {
+            const int tid = threadIdx.x;
+#pragma unroll
+            for (int it = 0; it < RegTile<TI>::NV; ++it) {
+                int i, k;
+                ki_map<TI>(it * NTHR + tid, i, k);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < nk && i < ni) {
+                    const T* q = p + (int64_t)i * si + (int64_t)k * sk;
+                    if (sizeof(T) == 4 && vec && i + 3 < ni) {
+                        v = __ldg(reinterpret_cast<const float4*>(q));
+                    } else {
+                        v.x = ld1(q);
+                        if (i + 1 < ni) v.y = ld1(q + si);
+                        if (i + 2 < ni) v.z = ld1(q + 2 * si);
+                        if (i + 3 < ni) v.w = ld1(q + 3 * si);
+                    }
+                }
+                r.v[it] = v;
+            }
+        }
+    }
+    static __device__ __forceinline__ float hi_part(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+    template <int TI, bool KI, class XF>
+    static __device__ __forceinline__ void store(const tc::Dst& d, const RegTile<TI>& r, XF xf) {
+        constexpr int LBO = tc::Geo<TI>::LBO;
+        const int tid = threadIdx.x;
+#pragma unroll
+        for (int it = 0; it < RegTile<TI>::NV; ++it) {
+            const int vid = it * NTHR + tid;
+            const float4 v = r.v[it];
+            if constexpr (!KI) {
+                const int k = (vid % (BK / 4)) * 4, i = vid / (BK / 4);
+                const int off = (k >> 2) * LBO + (i >> 3) * tc::SBO + (i & 7) * 16;
+                float4 t = make_float4(xf(i, k, v.x), xf(i, k + 1, v.y), xf(i, k + 2, v.z), xf(i, k + 3, v.w));
+                if (d.x3) {
+                    const float4 h = make_float4(hi_part(t.x), hi_part(t.y), hi_part(t.z), hi_part(t.w));
+                    *reinterpret_cast<float4*>(d.lo + off) = make_float4(t.x - h.x, t.y - h.y, t.z - h.z, t.w - h.w);
+                    t = h;
+                }
+                *reinterpret_cast<float4*>(d.hi + off) = t;
+            } else {
+                int i, k;
+                ki_map<TI>(vid, i, k);
+                const float t[4] = {xf(i, k, v.x), xf(i + 1, k, v.y), xf(i + 2, k, v.z), xf(i + 3, k, v.w)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int off = (k >> 2) * LBO + ((i + j) >> 3) * tc::SBO + ((i + j) & 7) * 16 + (k & 3) * 4;
+                    float a = t[j];
+                    if (d.x3) {
+                        const float h = hi_part(a);
+                        *reinterpret_cast<float*>(d.lo + off) = a - h;
+                        a = h;
+                    }
+                    *reinterpret_cast<float*>(d.hi + off) = a;
+                }
+            }
+        }
+    }
+    // call after every early-return of the CTA: allocates tensor memory, arms the barriers (contains a block barrier)
+    __device__ __forceinline__ void begin(Shared& sm) {
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::s32(&sm.tmem_slot)), "r"(tc::TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::s32(&sm.bar[0])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::s32(&sm.bar[1])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::s32(&sm.bar_done)) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem = sm.tmem_slot;
+        issued[0] = issued[1] = waited[0] = waited[1] = 0;
+        started = false;
+    }
+    template <bool KIA, bool KIB, class LA, class LB, class SA, class SB>
+    __device__ __forceinline__ void pass(Shared& sm, int nkt, bool x3, LA la, LB lb, SA sa, SB sb) {
+        if (nkt <= 0) return;
+        x3_ = x3;
+        RegTile<BM> ra;
+        RegTile<BN> rb;
+        la(0, ra);
+        lb(0, rb);
+        // D = F32, A = B = TF32, both K-major, M = 128, N = 64
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int kt = 0; kt < nkt; ++kt) {
+            const int buf = kt & 1;
+            if (issued[buf] > waited[buf]) {   // the MMAs that read this stage two tiles ago must be done
+                tc::mbar_wait(&sm.bar[buf], waited[buf] & 1);
+                ++waited[buf];
+            }
+            sa(kt, ra, tc::Dst{sm.Ahi[buf], sm.Alo[buf], x3});
+            sb(kt, rb, tc::Dst{sm.Bhi[buf], sm.Blo[buf], x3});
+            if (kt + 1 < nkt) {   // next tile's global loads fly while the tensor core works
+                la(kt + 1, ra);
+                lb(kt + 1, rb);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned ah = tc::s32(sm.Ahi[buf]), bh = tc::s32(sm.Bhi[buf]), al = tc::s32(sm.Alo[buf]), bl = tc::s32(sm.Blo[buf]);
+                constexpr unsigned LA_ = tc::Geo<BM>::LBO, LB_ = tc::Geo<BN>::LBO;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {   // one MMA = 8 TF32 along K = two 16-byte core columns
+                    const unsigned oa = ks * 2 * LA_, ob = ks * 2 * LB_;
+                    if (x3) {   // small terms first
+                        tc::umma_tf32(tmem, tc::make_desc(al + oa, LA_, tc::SBO), tc::make_desc(bh + ob, LB_, tc::SBO), idesc, started);
+                        tc::umma_tf32(tmem, tc::make_desc(ah + oa, LA_, tc::SBO), tc::make_desc(bl + ob, LB_, tc::SBO), idesc, 1u);
+                        tc::umma_tf32(tmem, tc::make_desc(ah + oa, LA_, tc::SBO), tc::make_desc(bh + ob, LB_, tc::SBO), idesc, 1u);
+                    } else {
+                        tc::umma_tf32(tmem, tc::make_desc(ah + oa, LA_, tc::SBO), tc::make_desc(bh + ob, LB_, tc::SBO), idesc, started);
+                    }
+                    started = true;
+                }
+                tc::umma_commit(&sm.bar[buf]);
+            }
+            started = true;
+            ++issued[buf];
+        }
+    }
+    // visit every accumulator element: fn(m, n, value&) -- thread = one row (TMEM lane), 32 consecutive columns
+    template <class F> __device__ __forceinline__ void for_each(Shared& sm, F fn) {
+        if (threadIdx.x == 0) tc::umma_commit(&sm.bar_done);
+        tc::mbar_wait(&sm.bar_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int m = (warp & 3) * 32 + lane, n0 = (warp >> 2) * 32;
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+            uint32_t v[8];
+            const uint32_t addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(n0 + c0);
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                         : "r"(addr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float f = started ? __uint_as_float(v[j]) : 0.f;
+                fn(m, n0 + c0 + j, f);
+            }
+        }
+    }
+    __device__ __forceinline__ void end(Shared& sm) {
+        (void)sm;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tc::TMEM_COLS));
+    }
+};
+
 __device__ __forceinline__ Smem& smem_ref() {
-    extern __shared__ __align__(16) unsigned char raw[];
+    extern __shared__ __align__(1024) unsigned char raw[];
     return *reinterpret_cast<Smem*>(raw);
 }
 
 // stage the (b, h, c) chunk's cs / dt' rows into shared memory buffer `hb`
-__device__ __forceinline__ void stage_cs(Smem& sm, int hb, const Ws& ws, const Dims& d, int b, int h, int c) {
+template <class S>
+__device__ __forceinline__ void stage_cs(S& sm, int hb, const Ws& ws, const Dims& d, int b, int h, int c) {
     const size_t off = (((size_t)b * d.H + h) * d.nc + c) * d.Q;
     for (int i = threadIdx.x; i < d.Q; i += NTHR) {
         sm.cs[hb][i] = ws.cs[off + i];
@@ -316,7 +582,8 @@ __device__ __forceinline__ void stage_cs(Smem& sm, int hb, const Ws& ws, const D
     }
 }
 
-__device__ __forceinline__ float block_sum(Smem& sm, float v) {
+template <class S>
+__device__ __forceinline__ float block_sum(S& sm, float v) {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
@@ -365,9 +632,9 @@ __global__ void __launch_bounds__(MAXQ) dt_cumsum_kernel(const T* dt, int64_t s0
 //   MODE 0 (chunk states):  src_x = x,    src_b = B,  w_s = exp(cs_Q - cs_s) dt'_s
 //   MODE 1 (d states):      src_x = dout, src_b = C,  w_s = exp(cs_s)
 // GEMM: M = n (128 per tile), N = p (64 per tile), K = s.
-template <typename T, int MODE>
+template <typename T, int MODE, class E>
 __global__ void __launch_bounds__(NTHR, 2) chunk_state_kernel(View4<T> X, View4<T> Bv, Dims d, Ws ws, float* out, int x3) {
-    Smem& sm = smem_ref();
+    typename E::Shared& sm = E::smem();
     const int ntn = (d.N + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
     int bid = blockIdx.x;
     const int tn = bid % ntn; bid /= ntn;
@@ -387,23 +654,23 @@ __global__ void __launch_bounds__(NTHR, 2) chunk_state_kernel(View4<T> X, View4<
     const T* pa = Bv.p + b * Bv.s0 + (int64_t)l0 * Bv.s1 + g * Bv.s2 + (int64_t)n0 * Bv.s3;   // (i = n, k = s)
     const T* pb = X.p + b * X.s0 + (int64_t)l0 * X.s1 + h * X.s2 + (int64_t)p0 * X.s3;        // (i = p, k = s)
     const bool va = vec_ok(pa, Bv.s1, Bv.s3), vb = vec_ok(pb, X.s1, X.s3);
-    Acc acc;
-    acc.zero();
-    gemm_pipeline(
-        sm, (q + BK - 1) / BK,
-        [&](int kt, RegTile<BM>& r) { load_raw<BM, false>(r, pa + (int64_t)kt * BK * Bv.s1, Bv.s3, Bv.s1, d.N - n0, q - kt * BK, va); },
-        [&](int kt, RegTile<BN>& r) { load_raw<BN, false>(r, pb + (int64_t)kt * BK * X.s1, X.s3, X.s1, d.P - p0, q - kt * BK, vb); },
-        [&](int, const RegTile<BM>& r, float* sA) { store_tile<BM, false>(sA, r, Identity()); },
-        [&](int kt, const RegTile<BN>& r, float* sB) {
+    E eng;
+    eng.begin(sm);
+    eng.template pass<false, false>(
+        sm, (q + BK - 1) / BK, x3 != 0,
+        [&](int kt, RegTile<BM>& r) { E::template load<BM, false>(r, pa + (int64_t)kt * BK * Bv.s1, Bv.s3, Bv.s1, d.N - n0, q - kt * BK, va); },
+        [&](int kt, RegTile<BN>& r) { E::template load<BN, false>(r, pb + (int64_t)kt * BK * X.s1, X.s3, X.s1, d.P - p0, q - kt * BK, vb); },
+        [&](int, const RegTile<BM>& r, auto sA) { E::template store<BM, false>(sA, r, Identity()); },
+        [&](int kt, const RegTile<BN>& r, auto sB) {
             const float* w = sm.v1[0] + kt * BK;
-            store_tile<BN, false>(sB, r, [&](int, int k, float v) { return v * w[k]; });
-        },
-        [&](const float* sA, const float* sB) { warp_mma<false, false>(acc, sA, sB, x3 != 0); });
+            E::template store<BN, false>(sB, r, [&](int, int k, float v) { return v * w[k]; });
+        });
     float* o = out + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
-    for_each_acc(acc, [&](int m, int n, float& v) {
+    eng.for_each(sm, [&](int m, int n, float& v) {
         const int nn = n0 + m, p = p0 + n;
         if (nn < d.N && p < d.P) o[(size_t)p * d.N + nn] = v;
     });
+    eng.end(sm);
 }
 
 // ---- K3: state passing over chunks (in place: local states -> chunk-entry states) --------------
@@ -457,9 +724,9 @@ __global__ void state_pass_kernel_scalar(Dims d, Ws ws, const float* init, float
 }
 
 // ---- K4: CB[l][s] = sum_n C[l, n] B[s, n]  per (b, c, g); only tiles touching s <= l ------------
-template <typename T>
+template <typename T, class E>
 __global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, Dims d, Ws ws, int x3) {
-    Smem& sm = smem_ref();
+    typename E::Shared& sm = E::smem();
     const int ntm = (d.Q + BM - 1) / BM, ntn = (d.Q + BN - 1) / BN;
     int bid = blockIdx.x;
     const int tn = bid % ntn; bid /= ntn;
@@ -473,20 +740,20 @@ __global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, D
     const T* pa = Cv.p + b * Cv.s0 + (int64_t)(l0 + m0) * Cv.s1 + g * Cv.s2;   // (i = l, k = n)
     const T* pb = Bv.p + b * Bv.s0 + (int64_t)(l0 + s0) * Bv.s1 + g * Bv.s2;   // (i = s, k = n)
     const bool va = vec_ok(pa, Cv.s1, Cv.s3), vb = vec_ok(pb, Bv.s1, Bv.s3);
-    Acc acc;
-    acc.zero();
-    gemm_pipeline(
-        sm, (d.N + BK - 1) / BK,
-        [&](int kt, RegTile<BM>& r) { load_raw<BM, true>(r, pa + (int64_t)kt * BK * Cv.s3, Cv.s1, Cv.s3, q - m0, d.N - kt * BK, va); },
-        [&](int kt, RegTile<BN>& r) { load_raw<BN, true>(r, pb + (int64_t)kt * BK * Bv.s3, Bv.s1, Bv.s3, q - s0, d.N - kt * BK, vb); },
-        [&](int, const RegTile<BM>& r, float* sA) { store_tile<BM, true>(sA, r, Identity()); },
-        [&](int, const RegTile<BN>& r, float* sB) { store_tile<BN, true>(sB, r, Identity()); },
-        [&](const float* sA, const float* sB) { warp_mma<true, true>(acc, sA, sB, x3 != 0); });
+    E eng;
+    eng.begin(sm);
+    eng.template pass<true, true>(
+        sm, (d.N + BK - 1) / BK, x3 != 0,
+        [&](int kt, RegTile<BM>& r) { E::template load<BM, true>(r, pa + (int64_t)kt * BK * Cv.s3, Cv.s1, Cv.s3, q - m0, d.N - kt * BK, va); },
+        [&](int kt, RegTile<BN>& r) { E::template load<BN, true>(r, pb + (int64_t)kt * BK * Bv.s3, Bv.s1, Bv.s3, q - s0, d.N - kt * BK, vb); },
+        [&](int, const RegTile<BM>& r, auto sA) { E::template store<BM, true>(sA, r, Identity()); },
+        [&](int, const RegTile<BN>& r, auto sB) { E::template store<BN, true>(sB, r, Identity()); });
     float* o = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
-    for_each_acc(acc, [&](int m, int n, float& v) {
+    eng.for_each(sm, [&](int m, int n, float& v) {
         const int l = m0 + m, s = s0 + n;
         if (l < q && s < q) o[(size_t)l * d.Q + s] = v;
     });
+    eng.end(sm);
 }
 
 // ---- K5: y = (CB o decay) (dt' x) + exp(cs) C Sin^T + D x   per (b, c, h) ------------------------
@@ -494,10 +761,10 @@ __global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, D
 // 32-wide k-tile it is the product of two factors <= 1 (reference point: cs at the end of the k-tile), one
 // per row and one per column, precomputed once per CTA; inside the 32 x 32 diagonal block it is evaluated
 // exactly per element (no overflow whatever the decay rate).
-template <typename T>
+template <typename T, class E>
 __global__ void __launch_bounds__(NTHR, 2) chunk_scan_kernel(View4<T> X, View4<T> Cv, const float* D, Dims d, Ws ws, T* out,
                                                              int64_t o0, int64_t o1, int64_t o2, int64_t o3, int has_init, int x3) {
-    Smem& sm = smem_ref();
+    typename E::Shared& sm = E::smem();
     const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
     int bid = blockIdx.x;
     const int tp = bid % ntp; bid /= ntp;
@@ -526,45 +793,44 @@ __global__ void __launch_bounds__(NTHR, 2) chunk_scan_kernel(View4<T> X, View4<T
     const float* cb = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q + (size_t)m0 * d.Q;   // (i = l, k = s)
     const T* px = X.p + b * X.s0 + (int64_t)l0 * X.s1 + h * X.s2 + (int64_t)p0 * X.s3;                      // (i = p, k = s)
     const bool va = vec_ok(cb, 1, d.Q), vb = vec_ok(px, X.s1, X.s3);
-    Acc acc;
-    acc.zero();
-    gemm_pipeline(
-        sm, nkt1,
-        [&](int kt, RegTile<BM>& r) { load_raw<BM, false>(r, cb + kt * BK, d.Q, 1, q - m0, send - kt * BK, va); },
-        [&](int kt, RegTile<BN>& r) { load_raw<BN, false>(r, px + (int64_t)kt * BK * X.s1, X.s3, X.s1, d.P - p0, q - kt * BK, vb); },
-        [&](int kt, const RegTile<BM>& r, float* sA) {
+    E eng;
+    eng.begin(sm);
+    eng.template pass<false, false>(
+        sm, nkt1, x3 != 0,
+        [&](int kt, RegTile<BM>& r) { E::template load<BM, false>(r, cb + kt * BK, d.Q, 1, q - m0, send - kt * BK, va); },
+        [&](int kt, RegTile<BN>& r) { E::template load<BN, false>(r, px + (int64_t)kt * BK * X.s1, X.s3, X.s1, d.P - p0, q - kt * BK, vb); },
+        [&](int kt, const RegTile<BM>& r, auto sA) {
             const int k0 = kt * BK;
-            store_tile<BM, false>(sA, r, [&](int i, int k, float v) {
+            E::template store<BM, false>(sA, r, [&](int i, int k, float v) {
                 const int l = m0 + i, s = k0 + k;
                 if (s > l) return 0.f;
                 if (l < k0 + BK) return v * exp_acc(sm.cs[0][l] - sm.cs[0][s]) * sm.dtp[0][s];
                 return v * sm.rowf[kt][i] * sm.v1[0][s];
             });
         },
-        [&](int, const RegTile<BN>& r, float* sB) { store_tile<BN, false>(sB, r, Identity()); },
-        [&](const float* sA, const float* sB) { warp_mma<false, false>(acc, sA, sB, x3 != 0); });
+        [&](int, const RegTile<BN>& r, auto sB) { E::template store<BN, false>(sB, r, Identity()); });
     if (c > 0 || has_init) {  // contribution of the chunk-entry state (identically zero for the first chunk without initial_states)
         const T* pc = Cv.p + b * Cv.s0 + (int64_t)(l0 + m0) * Cv.s1 + g * Cv.s2;                                   // (i = l, k = n)
         const float* Sin = ws.states + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N + (size_t)p0 * d.N;   // (i = p, k = n)
         const bool vc = vec_ok(pc, Cv.s1, Cv.s3), vs = vec_ok(Sin, 1, d.N);
-        gemm_pipeline(
-            sm, (d.N + BK - 1) / BK,
-            [&](int kt, RegTile<BM>& r) { load_raw<BM, true>(r, pc + (int64_t)kt * BK * Cv.s3, Cv.s1, Cv.s3, q - m0, d.N - kt * BK, vc); },
-            [&](int kt, RegTile<BN>& r) { load_raw<BN, false>(r, Sin + kt * BK, d.N, 1, d.P - p0, d.N - kt * BK, vs); },
-            [&](int, const RegTile<BM>& r, float* sA) {
-                store_tile<BM, true>(sA, r, [&](int i, int, float v) { return v * sm.v2[0][min(m0 + i, d.Q - 1)]; });
+        eng.template pass<true, false>(
+        sm, (d.N + BK - 1) / BK, x3 != 0,
+            [&](int kt, RegTile<BM>& r) { E::template load<BM, true>(r, pc + (int64_t)kt * BK * Cv.s3, Cv.s1, Cv.s3, q - m0, d.N - kt * BK, vc); },
+            [&](int kt, RegTile<BN>& r) { E::template load<BN, false>(r, Sin + kt * BK, d.N, 1, d.P - p0, d.N - kt * BK, vs); },
+            [&](int, const RegTile<BM>& r, auto sA) {
+                E::template store<BM, true>(sA, r, [&](int i, int, float v) { return v * sm.v2[0][min(m0 + i, d.Q - 1)]; });
             },
-            [&](int, const RegTile<BN>& r, float* sB) { store_tile<BN, false>(sB, r, Identity()); },
-            [&](const float* sA, const float* sB) { warp_mma<true, false>(acc, sA, sB, x3 != 0); });
+            [&](int, const RegTile<BN>& r, auto sB) { E::template store<BN, false>(sB, r, Identity()); });
     }
     const float Dh = D ? __ldg(D + h) : 0.f;
-    for_each_acc(acc, [&](int m, int n, float& v) {
+    eng.for_each(sm, [&](int m, int n, float& v) {
         const int l = m0 + m, p = p0 + n;
         if (l < q && p < d.P) {
             const float y = v + Dh * X.at(b, l0 + l, h, p);
             out[b * o0 + (l0 + l) * o1 + h * o2 + p * o3] = from_f32<T>(y);
         }
     });
+    eng.end(sm);
 }
 
 // ---- B2: reverse state passing: dstates[c] (off-diagonal adjoint) -> G[c] = adjoint of Sin[c+1];
@@ -1036,27 +1302,37 @@ static int validate(const b200_ssd_fwd_params* p) {
 }
 
 template <class K>
-static int set_smem(K kernel) {
-    static thread_local const void* done[32];
+static int set_smem(K kernel, size_t bytes = sizeof(Smem)) {
+    static thread_local const void* done[64];
     static thread_local int ndone = 0;
     for (int i = 0; i < ndone; ++i)
         if (done[i] == (const void*)kernel) return 0;
-    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    bytes = sizeof(tc::Shared) > sizeof(Smem) ? sizeof(tc::Shared) : sizeof(Smem);   // upper bound only; occupancy follows the launch's size
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    if (ndone < 32) done[ndone++] = (const void*)kernel;
+    if (ndone < 64) done[ndone++] = (const void*)kernel;
     return 0;
 }
 
 #define LAUNCH(kernel, grid, block, smem, st, ...)                  \
     do {                                                            \
         if ((smem) > 0)                                             \
-            if (int rc_ = set_smem(kernel)) return rc_;             \
+            if (int rc_ = set_smem(kernel, (smem))) return rc_;     \
         kernel<<<(unsigned)(grid), (block), (smem), (st)>>>(__VA_ARGS__); \
         if (int rc_ = check_launch(#kernel)) return rc_;            \
     } while (0)
+
+// tcgen05 / TMEM engine for the forward contractions (B200_SSD_TC=0 selects the mma.sync tiles)
+static bool use_tcgen05() {
+    static const bool on = [] {
+        const char* e = getenv("B200_SSD_TC");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 template <typename T>
 static int fwd_impl(const b200_ssd_fwd_params* p, cudaStream_t st) {
@@ -1069,7 +1345,10 @@ static int fwd_impl(const b200_ssd_fwd_params* p, cudaStream_t st) {
     const int ntn128 = (d.N + BM - 1) / BM, ntp64 = (d.P + BN - 1) / BN;
     LAUNCH((dt_cumsum_kernel<T>), (size_t)d.batch * d.H * d.nc, d.Q, 0, st, (const T*)p->dt, p->dt_stride[0], p->dt_stride[1],
            p->dt_stride[2], p->A, p->dt_bias, p->dt_softplus, p->dt_min, p->dt_max, d, ws);
-    LAUNCH((chunk_state_kernel<T, 0>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, X, Bv, d, ws, ws.states, x3);
+    const bool tcg = use_tcgen05();
+    const size_t SMT = x3 ? tc::SMEM_X3 : tc::SMEM_TF32;
+    if (tcg) LAUNCH((chunk_state_kernel<T, 0, TcEngine>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SMT, st, X, Bv, d, ws, ws.states, x3);
+    else LAUNCH((chunk_state_kernel<T, 0, MmaEngine>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, X, Bv, d, ws, ws.states, x3);
     {
         const size_t PN = (size_t)d.P * d.N;
         const bool vec = PN % 4 == 0 && ((uintptr_t)ws.states & 15) == 0 && ((uintptr_t)p->initial_states & 15) == 0 &&
@@ -1083,9 +1362,15 @@ static int fwd_impl(const b200_ssd_fwd_params* p, cudaStream_t st) {
             LAUNCH(state_pass_kernel_scalar, (n + 255) / 256, 256, 0, st, d, ws, p->initial_states, p->final_states);
         }
     }
-    LAUNCH((cb_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, Cv, Bv, d, ws, x3);
-    LAUNCH((chunk_scan_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Cv, p->D, d, ws, (T*)p->out,
-           p->out_stride[0], p->out_stride[1], p->out_stride[2], p->out_stride[3], p->initial_states != nullptr, x3);
+    if (tcg) {
+        LAUNCH((cb_kernel<T, TcEngine>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SMT, st, Cv, Bv, d, ws, x3);
+        LAUNCH((chunk_scan_kernel<T, TcEngine>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SMT, st, X, Cv, p->D, d, ws, (T*)p->out,
+               p->out_stride[0], p->out_stride[1], p->out_stride[2], p->out_stride[3], p->initial_states != nullptr, x3);
+    } else {
+        LAUNCH((cb_kernel<T, MmaEngine>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, Cv, Bv, d, ws, x3);
+        LAUNCH((chunk_scan_kernel<T, MmaEngine>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Cv, p->D, d, ws, (T*)p->out,
+               p->out_stride[0], p->out_stride[1], p->out_stride[2], p->out_stride[3], p->initial_states != nullptr, x3);
+    }
     return 0;
 }
 
@@ -1126,7 +1411,11 @@ static int bwd_impl(const b200_ssd_bwd_params* q, cudaStream_t st) {
         set_error("b200_ssd_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    LAUNCH((chunk_state_kernel<T, 1>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, DO, Cv, d, ws, sc.dstates, x3);
+    if (use_tcgen05())
+        LAUNCH((chunk_state_kernel<T, 1, TcEngine>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, (x3 ? tc::SMEM_X3 : tc::SMEM_TF32), st,
+               DO, Cv, d, ws, sc.dstates, x3);
+    else
+        LAUNCH((chunk_state_kernel<T, 1, MmaEngine>), (size_t)d.batch * d.nc * d.H * ntp64 * ntn128, NTHR, SM, st, DO, Cv, d, ws, sc.dstates, x3);
     {
         const size_t PN = (size_t)d.P * d.N;
         const bool vec = PN % 4 == 0 && ((uintptr_t)ws.states & 15) == 0 && ((uintptr_t)sc.dstates & 15) == 0 &&
