@@ -434,6 +434,17 @@ struct TcEngine {
             }
         }
     }
+    // run-time choice of the mapping: ki = "i is the contiguous dimension of the source"
+    template <int TI, typename T>
+    static __device__ __forceinline__ void load_any(RegTile<TI>& r, const T* p, int64_t si, int64_t sk, int ni, int nk, bool ki) {
+        if (ki) load<TI, true>(r, p, si, sk, ni, nk, vec_ok(p, si, sk));
+        else load<TI, false>(r, p, si, sk, ni, nk, vec_ok(p, sk, si));
+    }
+    template <int TI, class XF>
+    static __device__ __forceinline__ void store_any(const tc::Dst& d, const RegTile<TI>& r, bool ki, XF xf) {
+        if (ki) store<TI, true>(d, r, xf);
+        else store<TI, false>(d, r, xf);
+    }
     static __device__ __forceinline__ float hi_part(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
     template <int TI, bool KI, class XF>
     static __device__ __forceinline__ void store(const tc::Dst& d, const RegTile<TI>& r, XF xf) {
@@ -1022,6 +1033,86 @@ __global__ void __launch_bounds__(NTHR, 2) dx_kernel(View4<T> X, View4<T> Bv, Vi
     }
 }
 
+// B3 on the tcgen05 engine: same contractions, operands staged through registers (128-bit loads where the view
+// allows) into UMMA tiles, accumulator row = one thread in the epilogue (row sums need no shuffles).
+template <typename T>
+__global__ void __launch_bounds__(NTHR, 2) dx_kernel_tc(View4<T> X, View4<T> Bv, View4<T> DO, View4<T> OUT, const float* D, Dims d, Ws ws,
+                                                        const float* G, float* dx, float* ddtp_exp, float* dcs_pos, float* dD, int x3) {
+    using E = TcEngine;
+    E::Shared& sm = E::smem();
+    const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int tp = bid % ntp; bid /= ntp;
+    const int tm = bid % ntm; bid /= ntm;
+    const int h = bid % d.H; bid /= d.H;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int g = h / d.hpg;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int m0 = tm * BM, p0 = tp * BN;
+    if (m0 >= q) return;
+    stage_cs(sm, 0, ws, d, b, h, c);
+    __syncthreads();
+    const float csQ = sm.cs[0][d.Q - 1];
+    const float* cb = ws.cb + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
+    const float* Gs = G + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
+    E eng;
+    eng.begin(sm);
+    {   // Z += (CB o decay)^T dout : A(i = s, k = l) = CB[l][s] exp(cs_l - cs_s) for s <= l,  B(i = p, k = l) = dout[l][p]
+        const int kb = (m0 / BK) * BK;
+        const T* pdo = DO.p + b * DO.s0 + (int64_t)(l0 + kb) * DO.s1 + h * DO.s2 + (int64_t)p0 * DO.s3;
+        const bool kib = DO.s3 == 1;
+        eng.template pass<true, false>(
+            sm, (q - kb + BK - 1) / BK, x3 != 0,
+            [&](int kt, RegTile<BM>& r) { E::template load_any<BM>(r, cb + (size_t)(kb + kt * BK) * d.Q + m0, 1, d.Q, q - m0, q - kb - kt * BK, true); },
+            [&](int kt, RegTile<BN>& r) { E::template load_any<BN>(r, pdo + (int64_t)kt * BK * DO.s1, DO.s3, DO.s1, d.P - p0, q - kb - kt * BK, kib); },
+            [&](int kt, const RegTile<BM>& r, const tc::Dst& dst) {
+                const int k0 = kb + kt * BK;
+                E::template store_any<BM>(dst, r, true, [&](int i, int k, float v) {
+                    const int sidx = m0 + i, l = k0 + k;
+                    return (l < q && sidx <= l) ? v * exp_acc(sm.cs[0][l] - sm.cs[0][sidx]) : 0.f;
+                });
+            },
+            [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, kib, Identity()); });
+    }
+    if (c + 1 < d.nc) {   // Z += exp(cs_Q - cs_s) B G^T (G of the last chunk is identically zero)
+        const T* pbv = Bv.p + b * Bv.s0 + (int64_t)(l0 + m0) * Bv.s1 + g * Bv.s2;
+        const bool kia = Bv.s1 == 1;
+        eng.template pass<true, false>(
+            sm, (d.N + BK - 1) / BK, x3 != 0,
+            [&](int kt, RegTile<BM>& r) { E::template load_any<BM>(r, pbv + (int64_t)kt * BK * Bv.s3, Bv.s1, Bv.s3, q - m0, d.N - kt * BK, kia); },
+            [&](int kt, RegTile<BN>& r) { E::template load_any<BN>(r, Gs + (size_t)p0 * d.N + kt * BK, d.N, 1, d.P - p0, d.N - kt * BK, false); },
+            [&](int, const RegTile<BM>& r, const tc::Dst& dst) {
+                E::template store_any<BM>(dst, r, kia, [&](int i, int, float v) { return v * exp_acc(csQ - sm.cs[0][min(m0 + i, d.Q - 1)]); });
+            },
+            [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, false, Identity()); });
+    }
+    const float Dh = D ? __ldg(D + h) : 0.f;
+    float r1 = 0.f, r2 = 0.f, dDl = 0.f;
+    int srow = -1;
+    eng.for_each(sm, [&](int m, int n, float& z) {
+        const int sidx = m0 + m, pp = p0 + n;
+        srow = sidx;
+        if (sidx < q && pp < d.P) {
+            const float xv = X.at(b, l0 + sidx, h, pp), dv = DO.at(b, l0 + sidx, h, pp), ov = OUT.at(b, l0 + sidx, h, pp);
+            dx[(((size_t)b * d.L + l0 + sidx) * d.H + h) * d.P + pp] = sm.dtp[0][sidx] * z + Dh * dv;
+            r1 += xv * z;
+            r2 += dv * (ov - Dh * xv);
+            dDl += dv * xv;
+        }
+    });
+    if (srow >= 0 && srow < q) {   // one thread = one row (its 32 columns)
+        const size_t off = (((size_t)b * d.H + h) * d.nc + c) * d.Q + srow;
+        atomicAdd(ddtp_exp + off, r1);
+        atomicAdd(dcs_pos + off, r2);
+    }
+    if (dD) {
+        const float tot = block_sum(sm, dDl);
+        if (threadIdx.x == 0) atomicAdd(dD + h, tot);
+    }
+    eng.end(sm);
+}
+
 // ---- B4: dCB[l][s] = sum_{h in g} dt'_s exp(cs_l - cs_s) (dout_h x_h^T)[l, s],  s <= l ------------
 template <typename T>
 __global__ void __launch_bounds__(NTHR, 2) dcb_kernel(View4<T> X, View4<T> DO, Dims d, Ws ws, float* dcb, int x3) {
@@ -1160,6 +1251,86 @@ __global__ void __launch_bounds__(NTHR, 2) dbc_kernel(View4<T> X, View4<T> Bv, V
         const int l = m0 + m, nn = n0 + n;
         if (l < q && nn < d.N) o[(((size_t)b * d.L + l0 + l) * d.G + g) * d.N + nn] = v;
     });
+}
+
+// B5 on the tcgen05 engine.
+template <typename T>
+__global__ void __launch_bounds__(NTHR, 2) dbc_kernel_tc(View4<T> X, View4<T> Bv, View4<T> Cv, View4<T> DO, Dims d, Ws ws,
+                                                         const float* dcb_all, const float* G, float* dB, float* dC, int x3) {
+    using E = TcEngine;
+    E::Shared& sm = E::smem();
+    const int ntm = (d.Q + BM - 1) / BM, ntn = (d.N + BN - 1) / BN;
+    int bid = blockIdx.x;
+    const int which = bid & 1; bid >>= 1;  // 0: dC, 1: dB
+    const int tn = bid % ntn; bid /= ntn;
+    const int tm = bid % ntm; bid /= ntm;
+    const int g = bid % d.G; bid /= d.G;
+    const int c = bid % d.nc;
+    const int b = bid / d.nc;
+    const int q = min(d.Q, d.L - c * d.Q), l0 = c * d.Q;
+    const int m0 = tm * BM, n0 = tn * BN;
+    if (m0 >= q) return;
+    const float* dcb = dcb_all + (((size_t)b * d.nc + c) * d.G + g) * (size_t)d.Q * d.Q;
+    E eng;
+    eng.begin(sm);
+    if (which == 0) {   // dC[l][n] += sum_{s <= l} dCB[l][s] B[s][n]:  A(i = l, k = s),  B(i = n, k = s)
+        const int send = min(q, m0 + BM);
+        const T* pb = Bv.p + b * Bv.s0 + (int64_t)l0 * Bv.s1 + g * Bv.s2 + (int64_t)n0 * Bv.s3;
+        const bool kib = Bv.s3 == 1;
+        eng.template pass<false, false>(
+            sm, (send + BK - 1) / BK, x3 != 0,
+            [&](int kt, RegTile<BM>& r) { E::template load_any<BM>(r, dcb + (size_t)m0 * d.Q + kt * BK, d.Q, 1, q - m0, send - kt * BK, false); },
+            [&](int kt, RegTile<BN>& r) { E::template load_any<BN>(r, pb + (int64_t)kt * BK * Bv.s1, Bv.s3, Bv.s1, d.N - n0, q - kt * BK, kib); },
+            [&](int kt, const RegTile<BM>& r, const tc::Dst& dst) {
+                const int k0 = kt * BK;
+                E::template store_any<BM>(dst, r, false, [&](int i, int k, float v) { return (k0 + k <= m0 + i) ? v : 0.f; });
+            },
+            [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, kib, Identity()); });
+    } else {            // dB[s][n] += sum_{l >= s} dCB[l][s] C[l][n]:  A(i = s, k = l),  B(i = n, k = l)
+        const int kb = (m0 / BK) * BK;
+        const T* pc = Cv.p + b * Cv.s0 + (int64_t)(l0 + kb) * Cv.s1 + g * Cv.s2 + (int64_t)n0 * Cv.s3;
+        const bool kib = Cv.s3 == 1;
+        eng.template pass<true, false>(
+            sm, (q - kb + BK - 1) / BK, x3 != 0,
+            [&](int kt, RegTile<BM>& r) { E::template load_any<BM>(r, dcb + (size_t)(kb + kt * BK) * d.Q + m0, 1, d.Q, q - m0, q - kb - kt * BK, true); },
+            [&](int kt, RegTile<BN>& r) { E::template load_any<BN>(r, pc + (int64_t)kt * BK * Cv.s1, Cv.s3, Cv.s1, d.N - n0, q - kb - kt * BK, kib); },
+            [&](int kt, const RegTile<BM>& r, const tc::Dst& dst) {
+                const int k0 = kb + kt * BK;
+                E::template store_any<BM>(dst, r, true, [&](int i, int k, float v) { return (m0 + i <= k0 + k) ? v : 0.f; });
+            },
+            [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, kib, Identity()); });
+    }
+    // state terms, head by head (K = p):  A(i = l, k = p) = src[l][p] w_l,  B(i = n, k = p) = S[p][n]
+    const View4<T>& Asrc = which == 0 ? DO : X;
+    const float* Sbase = which == 0 ? ws.states : G;
+    if (which == 0 || c + 1 < d.nc) {
+        const bool kia = Asrc.s1 == 1;
+        for (int hh = 0; hh < d.hpg; ++hh) {
+            const int h = g * d.hpg + hh, hb = hh & 1;
+            stage_cs(sm, hb, ws, d, b, h, c);
+            __syncthreads();
+            const float csQ = sm.cs[hb][d.Q - 1];
+            const float* S = Sbase + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
+            const T* pa = Asrc.p + b * Asrc.s0 + (int64_t)(l0 + m0) * Asrc.s1 + h * Asrc.s2;
+            eng.template pass<true, true>(
+                sm, (d.P + BK - 1) / BK, x3 != 0,
+                [&](int kt, RegTile<BM>& r) { E::template load_any<BM>(r, pa + (int64_t)kt * BK * Asrc.s3, Asrc.s1, Asrc.s3, q - m0, d.P - kt * BK, kia); },
+                [&](int kt, RegTile<BN>& r) { E::template load_any<BN>(r, S + (size_t)kt * BK * d.N + n0, 1, d.N, d.N - n0, d.P - kt * BK, true); },
+                [&](int, const RegTile<BM>& r, const tc::Dst& dst) {
+                    E::template store_any<BM>(dst, r, kia, [&](int i, int, float v) {
+                        const int l = min(m0 + i, d.Q - 1);
+                        return v * (which == 0 ? exp_acc(sm.cs[hb][l]) : exp_acc(csQ - sm.cs[hb][l]) * sm.dtp[hb][l]);
+                    });
+                },
+                [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, true, Identity()); });
+        }
+    }
+    float* o = which == 0 ? dC : dB;
+    eng.for_each(sm, [&](int m, int n, float& v) {
+        const int l = m0 + m, nn = n0 + n;
+        if (l < q && nn < d.N) o[(((size_t)b * d.L + l0 + l) * d.G + g) * d.N + nn] = v;
+    });
+    eng.end(sm);
 }
 
 // ---- B6: d cs -> d(dt' A) (reverse cumsum) -> ddt', dA, ddt, ddt_bias ----------------------------
@@ -1429,11 +1600,19 @@ static int bwd_impl(const b200_ssd_bwd_params* q, cudaStream_t st) {
             LAUNCH(state_pass_bwd_kernel_scalar, (size_t)d.batch * d.H * nblk, NTHR, 0, st, d, ws, sc.dstates, sc.dcsQ);
         }
     }
-    LAUNCH((dx_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Bv, DO, OUT, p->D, d, ws, sc.dstates, q->dx,
-           sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
+    if (use_tcgen05())
+        LAUNCH((dx_kernel_tc<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, (x3 ? tc::SMEM_X3 : tc::SMEM_TF32), st, X, Bv, DO, OUT, p->D,
+               d, ws, sc.dstates, q->dx, sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
+    else
+        LAUNCH((dx_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Bv, DO, OUT, p->D, d, ws, sc.dstates, q->dx,
+               sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
     LAUNCH((dcb_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, X, DO, d, ws, sc.dcb, x3);
-    LAUNCH((dbc_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntn64 * 2, NTHR, SM, st, X, Bv, Cv, DO, d, ws, sc.dcb, sc.dstates,
-           q->dB, q->dC, x3);
+    if (use_tcgen05())
+        LAUNCH((dbc_kernel_tc<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntn64 * 2, NTHR, (x3 ? tc::SMEM_X3 : tc::SMEM_TF32), st, X, Bv, Cv, DO, d,
+               ws, sc.dcb, sc.dstates, q->dB, q->dC, x3);
+    else
+        LAUNCH((dbc_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntn64 * 2, NTHR, SM, st, X, Bv, Cv, DO, d, ws, sc.dcb, sc.dstates,
+               q->dB, q->dC, x3);
     LAUNCH((dt_bwd_kernel<T>), (size_t)d.batch * d.H * d.nc, d.Q, 0, st, (const T*)p->dt, p->dt_stride[0], p->dt_stride[1],
            p->dt_stride[2], p->A, p->dt_bias, p->dt_softplus, p->dt_min, p->dt_max, d, ws, sc.ddtp_exp, sc.dcs_pos, sc.dcsQ, q->ddt,
            q->dA, q->ddt_bias);
