@@ -1076,6 +1076,8 @@ __global__ void __launch_bounds__(NTHR, 2) dx_kernel_tc(View4<T> X, View4<T> Bv,
             [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, kib, Identity()); });
     }
     if (c + 1 < d.nc) {   // Z += exp(cs_Q - cs_s) B G^T (G of the last chunk is identically zero)
+        if (threadIdx.x < BM) sm.v1[0][threadIdx.x] = exp_acc(csQ - sm.cs[0][min(m0 + (int)threadIdx.x, d.Q - 1)]);
+        __syncthreads();
         const T* pbv = Bv.p + b * Bv.s0 + (int64_t)(l0 + m0) * Bv.s1 + g * Bv.s2;
         const bool kia = Bv.s1 == 1;
         eng.template pass<true, false>(
@@ -1083,7 +1085,7 @@ __global__ void __launch_bounds__(NTHR, 2) dx_kernel_tc(View4<T> X, View4<T> Bv,
             [&](int kt, RegTile<BM>& r) { E::template load_any<BM>(r, pbv + (int64_t)kt * BK * Bv.s3, Bv.s1, Bv.s3, q - m0, d.N - kt * BK, kia); },
             [&](int kt, RegTile<BN>& r) { E::template load_any<BN>(r, Gs + (size_t)p0 * d.N + kt * BK, d.N, 1, d.P - p0, d.N - kt * BK, false); },
             [&](int, const RegTile<BM>& r, const tc::Dst& dst) {
-                E::template store_any<BM>(dst, r, kia, [&](int i, int, float v) { return v * exp_acc(csQ - sm.cs[0][min(m0 + i, d.Q - 1)]); });
+                E::template store_any<BM>(dst, r, kia, [&](int i, int, float v) { return v * sm.v1[0][i]; });
             },
             [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, false, Identity()); });
     }
@@ -1310,6 +1312,11 @@ __global__ void __launch_bounds__(NTHR, 2) dbc_kernel_tc(View4<T> X, View4<T> Bv
             stage_cs(sm, hb, ws, d, b, h, c);
             __syncthreads();
             const float csQ = sm.cs[hb][d.Q - 1];
+            if (threadIdx.x < BM) {   // the row factor, once per (head, row) instead of once per element
+                const int l = min(m0 + (int)threadIdx.x, d.Q - 1);
+                sm.v1[hb][threadIdx.x] = which == 0 ? exp_acc(sm.cs[hb][l]) : exp_acc(csQ - sm.cs[hb][l]) * sm.dtp[hb][l];
+            }
+            __syncthreads();
             const float* S = Sbase + (((size_t)b * d.nc + c) * d.H + h) * (size_t)d.P * d.N;
             const T* pa = Asrc.p + b * Asrc.s0 + (int64_t)(l0 + m0) * Asrc.s1 + h * Asrc.s2;
             eng.template pass<true, true>(
@@ -1317,10 +1324,7 @@ __global__ void __launch_bounds__(NTHR, 2) dbc_kernel_tc(View4<T> X, View4<T> Bv
                 [&](int kt, RegTile<BM>& r) { E::template load_any<BM>(r, pa + (int64_t)kt * BK * Asrc.s3, Asrc.s1, Asrc.s3, q - m0, d.P - kt * BK, kia); },
                 [&](int kt, RegTile<BN>& r) { E::template load_any<BN>(r, S + (size_t)kt * BK * d.N + n0, 1, d.N, d.N - n0, d.P - kt * BK, true); },
                 [&](int, const RegTile<BM>& r, const tc::Dst& dst) {
-                    E::template store_any<BM>(dst, r, kia, [&](int i, int, float v) {
-                        const int l = min(m0 + i, d.Q - 1);
-                        return v * (which == 0 ? exp_acc(sm.cs[hb][l]) : exp_acc(csQ - sm.cs[hb][l]) * sm.dtp[hb][l]);
-                    });
+                    E::template store_any<BM>(dst, r, kia, [&](int i, int, float v) { return v * sm.v1[hb][i]; });
                 },
                 [&](int, const RegTile<BN>& r, const tc::Dst& dst) { E::template store_any<BN>(dst, r, true, Identity()); });
         }
