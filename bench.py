@@ -421,7 +421,16 @@ def run_cuda(args):
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
     if ddp:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: ncclCommDestroy can block for minutes while captured step graphs still
+        # reference the communicator (seen at N=2: the JSON line was out, the ranks never exited).  Every rank has
+        # passed the final all-reduce of the timings, so nothing is in flight.
+        try:
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
 
 
 def main():
