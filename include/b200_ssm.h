@@ -214,6 +214,25 @@ int b200_rmsnorm_gated_bwd(const float* x, const float* z, const float* w, const
                            const float* dy, float* dx, float* dz, float* dw_partial /* (grid, dim) */,
                            int32_t dw_rows, int64_t rows, int32_t dim, b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SS2D output stage: out = LayerNorm(y) * silu(z) and its backward -- replaces
+ * `y = self.out_norm(y); y = y * F.silu(z)` (reference MedMamba.py:478-479; nn.LayerNorm(d_inner), eps 1e-5)
+ * and the four autograd kernels behind it.
+ *   y (rows, D) f32 contiguous (the cross-merge output); z (rows, D) with row stride z_row_stride (the second
+ *   half of in_proj's output, read in place), z_dtype in {F32, BF16}; w, b (D) f32; out (rows, D) out_dtype
+ *   in {F32, BF16 (= what the following Linear would cast to under autocast)}; mean, rstd (rows) f32 kept for
+ *   the backward.  Backward: dout (rows, D) out_dtype -> dy (rows, D) f32, dz (rows, D) z_dtype contiguous,
+ *   dw_partial / db_partial (b200_ln_gate_grid(rows), D) f32 per-CTA partial sums (the caller adds the rows up).
+ *   D <= 1024.
+ * ------------------------------------------------------------------------------------------ */
+int b200_ln_gate_grid(int64_t rows);
+int b200_ln_gate_fwd(const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w, const float* b,
+                     void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
+                     b200_stream_t stream);
+int b200_ln_gate_bwd(const void* dout, const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
+                     const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
+                     float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------ */
 const char* b200_last_error(void);   /* thread-local message of the last failing call */
 int b200_version(void);              /* ABI version, bumped on any struct change */

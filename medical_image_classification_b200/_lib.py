@@ -77,6 +77,7 @@ EXPORTS = [
     "b200_cross_scan_pack", "b200_cross_scan_pack_bwd", "b200_cross_merge", "b200_cross_merge_bwd",
     "b200_ssd_workspace_bytes", "b200_ssd_bwd_scratch_bytes", "b200_ssd_fwd", "b200_ssd_bwd",
     "b200_rmsnorm_gated_fwd", "b200_rmsnorm_gated_bwd",
+    "b200_ln_gate_grid", "b200_ln_gate_fwd", "b200_ln_gate_bwd",
     "b200_last_error", "b200_version", "b200_kernel_launches", "b200_sizeof_params",
 ]
 
@@ -116,6 +117,9 @@ def load() -> C.CDLL:
         getattr(lib, name).argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200_rmsnorm_gated_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, vp]
     lib.b200_rmsnorm_gated_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]
+    lib.b200_ln_gate_grid.argtypes = [i64]
+    lib.b200_ln_gate_fwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]
+    lib.b200_ln_gate_bwd.argtypes = [vp, vp, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp]
     for which, st in enumerate((SScanFwdParams, SScanBwdParams, SsdFwdParams, SsdBwdParams)):
         if lib.b200_sizeof_params(which) != C.sizeof(st):
             raise RuntimeError(f"libb200ssm ABI mismatch for {st.__name__}: "

@@ -1,0 +1,205 @@
+// lngate.cu -- SS2D output stage: out = LayerNorm(y) * silu(z), forward and backward, sm_100a.
+//
+// Replaces the three element-wise passes the reference runs after the cross-merge (reference MedMamba.py:478-479:
+// `y = self.out_norm(y); y = y * F.silu(z)`, LayerNorm over the d_inner channels, eps 1e-5) and their four autograd
+// kernels (layer-norm input grad, the gamma/beta reduction, silu backward, mul backward).  SURVEY.md section 8(f) rank 1.
+// HBM-bound streaming kernels: one warp per row, the row lives in registers (d_inner <= 1024), statistics by
+// warp shuffles, one read of y / z / dout and one write of each output per element; d(weight), d(bias) are
+// accumulated per lane over the rows of a warp, combined per CTA in shared memory and written as per-CTA partials.
+//
+//   xhat = (y - mean) * rstd      n = xhat * w + b      out = n * silu(z)
+//   dn = dout * silu(z)           dz = dout * n * sigmoid(z) * (1 + z * (1 - sigmoid(z)))
+//   dw = sum_rows dn * xhat       db = sum_rows dn
+//   dy = rstd * (dn*w - mean_D(dn*w) - xhat * mean_D(dn*w * xhat))
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int LG_MAXD = 1024;          // columns held in registers: 32 per lane
+constexpr int LG_WARPS = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename TZ, typename TO, int NPL>
+__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float* __restrict__ y, const TZ* __restrict__ z, int64_t z_row_stride,
+                                                                    const float* __restrict__ w, const float* __restrict__ b,
+                                                                    TO* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
+                                                                    int64_t rows, int D, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * LG_WARPS + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * LG_WARPS;
+    const float invD = 1.f / (float)D;   // w / b are re-read per row (L1-resident): the row itself needs the registers
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        float v[NPL];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int c = lane + 32 * k;
+            v[k] = c < D ? __ldcs(y + r * D + c) : 0.f;
+            s += v[k];
+        }
+        const float mu = warp_sum(s) * invD;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int c = lane + 32 * k;
+            const float dlt = c < D ? v[k] - mu : 0.f;
+            q += dlt * dlt;
+        }
+        const float rs = rsqrtf(warp_sum(q) * invD + eps);
+        if (lane == 0) {
+            mean[r] = mu;
+            rstd[r] = rs;
+        }
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int c = lane + 32 * k;
+            if (c < D) {
+                const float zz = ldg_stream(z + r * z_row_stride + c);
+                const float n = (v[k] - mu) * rs * __ldg(w + c) + __ldg(b + c);
+                stg_stream(out + r * D + c, n * zz * sigmoidf_(zz));
+            }
+        }
+    }
+}
+
+template <typename TZ, typename TO, int NPL>
+__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __restrict__ dout, const float* __restrict__ y,
+                                                                    const TZ* __restrict__ z, int64_t z_row_stride, const float* __restrict__ w,
+                                                                    const float* __restrict__ b, const float* __restrict__ mean,
+                                                                    const float* __restrict__ rstd, float* __restrict__ dy, TZ* __restrict__ dz,
+                                                                    float* __restrict__ dw_part, float* __restrict__ db_part, int64_t rows, int D) {
+    __shared__ float red[LG_WARPS][32 * NPL];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * LG_WARPS + wid, nwarps = (int64_t)gridDim.x * LG_WARPS;
+    float aw[NPL], ab[NPL];
+#pragma unroll
+    for (int k = 0; k < NPL; ++k) {
+        aw[k] = 0.f;
+        ab[k] = 0.f;
+    }
+    const float invD = 1.f / (float)D;
+    for (int64_t r = warp; r < rows; r += nwarps) {
+        const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+        float xh[NPL], g[NPL];   // xhat, dn * w
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int c = lane + 32 * k;
+            xh[k] = 0.f;
+            g[k] = 0.f;
+            if (c < D) {
+                const float yy = __ldcs(y + r * D + c);
+                const float zz = ldg_stream(z + r * z_row_stride + c);
+                const float go = ldg_stream(dout + r * D + c);
+                const float sg = sigmoidf_(zz);
+                const float wc = __ldg(w + c);
+                xh[k] = (yy - mu) * rs;
+                const float n = xh[k] * wc + __ldg(b + c);
+                const float dn = go * zz * sg;
+                stg_stream(dz + r * D + c, go * n * sg * (1.f + zz * (1.f - sg)));
+                aw[k] += dn * xh[k];
+                ab[k] += dn;
+                g[k] = dn * wc;
+                s1 += g[k];
+                s2 += g[k] * xh[k];
+            }
+        }
+        const float m1 = warp_sum(s1) * invD, m2 = warp_sum(s2) * invD;
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int c = lane + 32 * k;
+            if (c < D) __stcs(dy + r * D + c, rs * (g[k] - m1 - xh[k] * m2));
+        }
+    }
+    // d(weight), d(bias): combine the CTA's warps, write one partial row per CTA
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) red[wid][lane + 32 * k] = pass ? ab[k] : aw[k];
+        __syncthreads();
+        for (int c = threadIdx.x; c < D; c += LG_WARPS * 32) {
+            float sacc = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < LG_WARPS; ++ww) sacc += red[ww][c];
+            (pass ? db_part : dw_part)[(size_t)blockIdx.x * D + c] = sacc;
+        }
+        __syncthreads();
+    }
+}
+
+static int lg_grid(int64_t rows) {
+    const int64_t want = (rows + LG_WARPS - 1) / LG_WARPS;
+    return (int)(want < 148 * 4 ? (want < 1 ? 1 : want) : 148 * 4);
+}
+
+template <typename TZ, typename TO, int NPL>
+static int lg_fwd_launch(const void* y, const void* z, int64_t zs, const float* w, const float* b, void* out, float* mean, float* rstd,
+                         int64_t rows, int D, float eps, cudaStream_t st) {
+    ln_gate_fwd_kernel<TZ, TO, NPL><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const float*)y, (const TZ*)z, zs, w, b, (TO*)out, mean, rstd, rows, D,
+                                                                             eps);
+    return check_launch("ln_gate_fwd_kernel");
+}
+template <typename TZ, typename TO, int NPL>
+static int lg_bwd_launch(const void* dout, const void* y, const void* z, int64_t zs, const float* w, const float* b, const float* mean,
+                         const float* rstd, float* dy, void* dz, float* dwp, float* dbp, int64_t rows, int D, cudaStream_t st) {
+    ln_gate_bwd_kernel<TZ, TO, NPL><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const float*)y, (const TZ*)z, zs, w, b, mean, rstd,
+                                                                             dy, (TZ*)dz, dwp, dbp, rows, D);
+    return check_launch("ln_gate_bwd_kernel");
+}
+
+// dispatch on (z dtype, out dtype, columns per lane)
+#define LG_DISPATCH(FN, ...)                                                                  \
+    do {                                                                                      \
+        const int npl = (D + 31) / 32;                                                        \
+        if (z_dtype == B200_F32 && out_dtype == B200_F32) {                                   \
+            if (npl <= 4) return FN<float, float, 4>(__VA_ARGS__);                            \
+            if (npl <= 8) return FN<float, float, 8>(__VA_ARGS__);                            \
+            if (npl <= 16) return FN<float, float, 16>(__VA_ARGS__);                          \
+            if (npl <= 24) return FN<float, float, 24>(__VA_ARGS__);                          \
+            return FN<float, float, 32>(__VA_ARGS__);                                         \
+        }                                                                                     \
+        if (z_dtype == B200_BF16 && out_dtype == B200_BF16) {                                 \
+            if (npl <= 4) return FN<__nv_bfloat16, __nv_bfloat16, 4>(__VA_ARGS__);            \
+            if (npl <= 8) return FN<__nv_bfloat16, __nv_bfloat16, 8>(__VA_ARGS__);            \
+            if (npl <= 16) return FN<__nv_bfloat16, __nv_bfloat16, 16>(__VA_ARGS__);          \
+            if (npl <= 24) return FN<__nv_bfloat16, __nv_bfloat16, 24>(__VA_ARGS__);          \
+            return FN<__nv_bfloat16, __nv_bfloat16, 32>(__VA_ARGS__);                         \
+        }                                                                                     \
+        if (z_dtype == B200_BF16 && out_dtype == B200_F32) {                                  \
+            if (npl <= 4) return FN<__nv_bfloat16, float, 4>(__VA_ARGS__);                    \
+            if (npl <= 8) return FN<__nv_bfloat16, float, 8>(__VA_ARGS__);                    \
+            if (npl <= 16) return FN<__nv_bfloat16, float, 16>(__VA_ARGS__);                  \
+            if (npl <= 24) return FN<__nv_bfloat16, float, 24>(__VA_ARGS__);                  \
+            return FN<__nv_bfloat16, float, 32>(__VA_ARGS__);                                 \
+        }                                                                                     \
+        B200_REQUIRE(false, "b200_ln_gate: unsupported dtype combination z=%d out=%d", z_dtype, out_dtype); \
+    } while (0)
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_ln_gate_grid(int64_t rows) { return lg_grid(rows); }
+
+extern "C" int b200_ln_gate_fwd(const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w, const float* b,
+                                void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
+                                b200_stream_t stream) {
+    B200_REQUIRE(y && z && w && b && out && mean && rstd, "b200_ln_gate_fwd: NULL argument");
+    B200_REQUIRE(rows >= 0 && D >= 1 && D <= LG_MAXD, "b200_ln_gate_fwd: D = %d outside [1, %d]", D, LG_MAXD);
+    if (rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    LG_DISPATCH(lg_fwd_launch, y, z, z_row_stride, w, b, out, mean, rstd, rows, D, eps, st);
+}
+
+extern "C" int b200_ln_gate_bwd(const void* dout, const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
+                                const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
+                                float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream) {
+    B200_REQUIRE(dout && y && z && w && b && mean && rstd && dy && dz && dw_partial && db_partial, "b200_ln_gate_bwd: NULL argument");
+    B200_REQUIRE(rows >= 1 && D >= 1 && D <= LG_MAXD, "b200_ln_gate_bwd: D = %d outside [1, %d]", D, LG_MAXD);
+    cudaStream_t st = (cudaStream_t)stream;
+    LG_DISPATCH(lg_bwd_launch, dout, y, z, z_row_stride, w, b, mean, rstd, dy, dz, dw_partial, db_partial, rows, D, st);
+}

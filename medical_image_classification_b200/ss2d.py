@@ -67,6 +67,70 @@ class _ProjFn(torch.autograd.Function):
         return dW, dX, None
 
 
+class LnGateFn(torch.autograd.Function):
+    """out = LayerNorm(y) * silu(z) in one pass over HBM (csrc/lngate.cu) -- reference MedMamba.py:478-479.
+    y (..., D) fp32; z (..., D) fp32 or bf16, only its last dimension has to be contiguous (it is the second half of
+    in_proj's output and is read in place); returns out_dtype (bf16 under autocast = what out_proj casts to)."""
+
+    @staticmethod
+    def forward(ctx, y, z, weight, bias, eps, out_dtype):
+        from . import _lib
+        _lib.require_cuda(y, z, weight, bias)
+        lib = _lib.load()
+        D = y.shape[-1]
+        y2 = y.reshape(-1, D)
+        if y2.dtype != torch.float32 or not y2.is_contiguous():
+            y2 = y2.float().contiguous()
+        z2 = z.reshape(-1, D) if z.is_contiguous() else None
+        if z2 is None:   # a strided view with contiguous rows: keep it in place
+            zs = z.stride(-2) if z.dim() >= 2 else D
+            ok = z.stride(-1) == 1 and all(z.stride(i) == z.stride(i + 1) * z.shape[i + 1] for i in range(z.dim() - 2))
+            z2 = z if ok else z.contiguous()
+            zs = zs if ok else D
+        else:
+            zs = D
+        if z2.dtype not in (torch.float32, torch.bfloat16):
+            z2, zs = z2.float().contiguous(), D
+        rows = y2.shape[0]
+        w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        out = torch.empty((rows, D), dtype=out_dtype, device=y.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=y.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            _lib.check(lib.b200_ln_gate_fwd(y2.data_ptr(), z2.data_ptr(), zs, _lib.dtype_code(z2.dtype), w32.data_ptr(), b32.data_ptr(),
+                                            out.data_ptr(), _lib.dtype_code(out_dtype), mean.data_ptr(), rstd.data_ptr(), rows, D, float(eps),
+                                            _lib.stream_ptr(y.device)), "b200_ln_gate_fwd")
+        ctx.save_for_backward(y2, z2, w32, b32, mean, rstd)
+        ctx.zs, ctx.shape, ctx.zshape = zs, y.shape, z.shape
+        ctx.wdtype, ctx.bdtype = weight.dtype, bias.dtype
+        return out.view(*y.shape[:-1], D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import _lib
+        lib = _lib.load()
+        y2, z2, w32, b32, mean, rstd = ctx.saved_tensors
+        rows, D = y2.shape
+        dout = dout.reshape(rows, D).contiguous()
+        dy = torch.empty_like(y2)
+        dz = torch.empty((rows, D), dtype=z2.dtype, device=y2.device)
+        grid = lib.b200_ln_gate_grid(rows)
+        part = torch.empty((2, grid, D), dtype=torch.float32, device=y2.device)
+        with torch.cuda.device(y2.device):
+            _lib.check(lib.b200_ln_gate_bwd(dout.data_ptr(), y2.data_ptr(), z2.data_ptr(), ctx.zs, _lib.dtype_code(z2.dtype), w32.data_ptr(),
+                                            b32.data_ptr(), _lib.dtype_code(dout.dtype), mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(),
+                                            dz.data_ptr(), part[0].data_ptr(), part[1].data_ptr(), rows, D, _lib.stream_ptr(y2.device)),
+                       "b200_ln_gate_bwd")
+        dwb = part.sum(1)
+        return dy.view(ctx.shape), dz.view(ctx.zshape), dwb[0].to(ctx.wdtype), dwb[1].to(ctx.bdtype), None, None
+
+
+def ln_gate(y, z, norm: nn.LayerNorm):
+    """LayerNorm(y) * silu(z) through libb200ssm (CUDA only)."""
+    out_dtype = torch.bfloat16 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else torch.float32
+    return LnGateFn.apply(y, z, norm.weight, norm.bias, norm.eps, out_dtype)
+
+
 class SS2D(nn.Module):
     def __init__(self, d_model, d_state=16, d_conv=3, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
                  dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, dropout=0.0, conv_bias=True, bias=False,
@@ -180,8 +244,11 @@ class SS2D(nn.Module):
         x = self.act(self.conv2d(x))
         y = self.forward_core(x)                                    # (B, H, W, D) fp32
         assert y.dtype == torch.float32
-        y = self.out_norm(y)
-        y = y * F.silu(z)
+        if y.is_cuda and self.d_inner <= 1024 and z.dtype in (torch.float32, torch.bfloat16):
+            y = ln_gate(y, z, self.out_norm)                        # out_norm + silu(z) gate, one pass (csrc/lngate.cu)
+        else:   # CPU data flow (oracle/cpu_path.py binds forward_core): the reference's two ops
+            y = self.out_norm(y)
+            y = y * F.silu(z)
         out = self.out_proj(y)
         if self.dropout is not None:
             out = self.dropout(out)
