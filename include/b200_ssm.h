@@ -233,6 +233,22 @@ int b200_ln_gate_bwd(const void* dout, const float* y, const void* z, int64_t z_
                      const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
                      float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SS2D producer stage: x = SiLU(depthwise conv3x3(x_in) + bias) -- replaces
+ * `x.permute(0,3,1,2).contiguous()`, `self.act(self.conv2d(x))` (reference MedMamba.py:470-473; Conv2d(D, D, 3,
+ * padding=1, groups=D)) and the `.float()` before the scan (MedMamba.py:403).
+ *   xin: channels-last (B, H, W, D) view, element (b,h,w,d) at ((b*H + h)*W + w)*pix_stride + d (the x half of
+ *   in_proj's output, pix_stride = 2 D), in_dtype in {F32, BF16}; weight (D, 3, 3) f32; bias (D) f32 or NULL;
+ *   out (B, D, H, W) f32 planes (what b200_cross_scan_pack reads).  W <= 64.
+ *   Backward: gout (B, D, H, W) f32 -> dxin (B, H, W, D) contiguous in_dtype; dweight (D, 9), dbias (D) f32 are
+ *   ACCUMULATED with atomics (the caller zero-fills them); dbias may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int b200_dwconv_silu_fwd(const void* xin, int64_t pix_stride, int32_t in_dtype, const float* weight, const float* bias, float* out,
+                         int32_t B, int32_t D, int32_t H, int32_t W, b200_stream_t stream);
+int b200_dwconv_silu_bwd(const float* gout, const void* xin, int64_t pix_stride, int32_t in_dtype, const float* weight,
+                         const float* bias, void* dxin, float* dweight, float* dbias, int32_t B, int32_t D, int32_t H, int32_t W,
+                         b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------ */
 const char* b200_last_error(void);   /* thread-local message of the last failing call */
 int b200_version(void);              /* ABI version, bumped on any struct change */

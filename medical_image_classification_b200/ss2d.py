@@ -125,6 +125,49 @@ class LnGateFn(torch.autograd.Function):
         return dy.view(ctx.shape), dz.view(ctx.zshape), dwb[0].to(ctx.wdtype), dwb[1].to(ctx.bdtype), None, None
 
 
+class DwConvSiluFn(torch.autograd.Function):
+    """x (B, D, H, W) fp32 = SiLU(depthwise conv3x3(xin) + bias) with xin a channels-last (B, H, W, D) view read in
+    place (csrc/dwconv.cu) -- reference MedMamba.py:470-473 + the .float() of :403."""
+
+    @staticmethod
+    def forward(ctx, xin, weight, bias):
+        from . import _lib
+        _lib.require_cuda(xin, weight, bias)
+        lib = _lib.load()
+        B, H, W, D = xin.shape
+        ok = xin.stride(3) == 1 and xin.stride(1) == W * xin.stride(2) and xin.stride(0) == H * xin.stride(1)
+        if not ok or xin.dtype not in (torch.float32, torch.bfloat16):
+            xin = xin.contiguous() if xin.dtype in (torch.float32, torch.bfloat16) else xin.float().contiguous()
+        w32 = weight.detach().float().reshape(D, 9).contiguous()
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        out = torch.empty((B, D, H, W), dtype=torch.float32, device=xin.device)
+        with torch.cuda.device(xin.device):
+            _lib.check(lib.b200_dwconv_silu_fwd(xin.data_ptr(), xin.stride(2), _lib.dtype_code(xin.dtype), w32.data_ptr(), _lib.ptr(b32),
+                                                out.data_ptr(), B, D, H, W, _lib.stream_ptr(xin.device)), "b200_dwconv_silu_fwd")
+        ctx.save_for_backward(xin, w32, b32)
+        ctx.wshape, ctx.wdtype = weight.shape, weight.dtype
+        ctx.bdtype = bias.dtype if bias is not None else None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        lib = _lib.load()
+        xin, w32, b32 = ctx.saved_tensors
+        B, H, W, D = xin.shape
+        g = g.float().contiguous()
+        dxin = torch.empty((B, H, W, D), dtype=xin.dtype, device=xin.device)
+        acc_w = torch.zeros((D * 9 + D,), dtype=torch.float32, device=xin.device)   # weight taps | bias: one memset
+        dw_buf, db_buf = acc_w[: D * 9], acc_w[D * 9:]
+        with torch.cuda.device(xin.device):
+            _lib.check(lib.b200_dwconv_silu_bwd(g.data_ptr(), xin.data_ptr(), xin.stride(2), _lib.dtype_code(xin.dtype), w32.data_ptr(),
+                                                _lib.ptr(b32), dxin.data_ptr(), dw_buf.data_ptr(), db_buf.data_ptr(), B, D, H, W,
+                                                _lib.stream_ptr(xin.device)), "b200_dwconv_silu_bwd")
+        dweight = dw_buf.view(ctx.wshape).to(ctx.wdtype)
+        dbias = db_buf.to(ctx.bdtype) if ctx.bdtype is not None else None
+        return dxin, dweight, dbias
+
+
 def ln_gate(y, z, norm: nn.LayerNorm):
     """LayerNorm(y) * silu(z) through libb200ssm (CUDA only)."""
     out_dtype = torch.bfloat16 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else torch.float32
@@ -240,8 +283,12 @@ class SS2D(nn.Module):
         B, H, W, C = x.shape
         xz = self.in_proj(x)
         x, z = xz.chunk(2, dim=-1)
-        x = x.permute(0, 3, 1, 2).contiguous()
-        x = self.act(self.conv2d(x))
+        if (x.is_cuda and self.d_conv == 3 and W <= 64 and x.dtype in (torch.float32, torch.bfloat16)
+                and self.forward_core == self.forward_core_fused):
+            x = DwConvSiluFn.apply(x, self.conv2d.weight, self.conv2d.bias)   # conv3x3 + SiLU, channels-last in -> fp32 planes out
+        else:   # the reference's ops (CPU data flow / API-path parity tests)
+            x = x.permute(0, 3, 1, 2).contiguous()
+            x = self.act(self.conv2d(x))
         y = self.forward_core(x)                                    # (B, H, W, D) fp32
         assert y.dtype == torch.float32
         if y.is_cuda and self.d_inner <= 1024 and z.dtype in (torch.float32, torch.bfloat16):
