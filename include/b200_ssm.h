@@ -218,7 +218,9 @@ int b200_rmsnorm_gated_bwd(const float* x, const float* z, const float* w, const
  * SS2D output stage: out = LayerNorm(y) * silu(z) and its backward -- replaces
  * `y = self.out_norm(y); y = y * F.silu(z)` (reference MedMamba.py:478-479; nn.LayerNorm(d_inner), eps 1e-5)
  * and the four autograd kernels behind it.
- *   y (rows, D) f32 contiguous (the cross-merge output); z (rows, D) with row stride z_row_stride (the second
+ *   z == NULL (and dz == NULL) gives the plain LayerNorm of the block's pre-norm (MedMamba.py:531 `self.ln_1`).
+ *   y (rows, D) f32 with row stride y_row_stride (the cross-merge output, or the right half of the block input read
+ *   in place); z (rows, D) with row stride z_row_stride (the second
  *   half of in_proj's output, read in place), z_dtype in {F32, BF16}; w, b (D) f32; out (rows, D) out_dtype
  *   in {F32, BF16 (= what the following Linear would cast to under autocast)}; mean, rstd (rows) f32 kept for
  *   the backward.  Backward: dout (rows, D) out_dtype -> dy (rows, D) f32, dz (rows, D) z_dtype contiguous,
@@ -226,11 +228,11 @@ int b200_rmsnorm_gated_bwd(const float* x, const float* z, const float* w, const
  *   D <= 1024.
  * ------------------------------------------------------------------------------------------ */
 int b200_ln_gate_grid(int64_t rows);
-int b200_ln_gate_fwd(const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w, const float* b,
-                     void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
+int b200_ln_gate_fwd(const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
+                     const float* b, void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
                      b200_stream_t stream);
-int b200_ln_gate_bwd(const void* dout, const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
-                     const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
+int b200_ln_gate_bwd(const void* dout, const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype,
+                     const float* w, const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
                      float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -121,8 +121,8 @@ def load() -> C.CDLL:
     lib.b200_dwconv_silu_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_dwconv_silu_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_ln_gate_grid.argtypes = [i64]
-    lib.b200_ln_gate_fwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]
-    lib.b200_ln_gate_bwd.argtypes = [vp, vp, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.b200_ln_gate_fwd.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]
+    lib.b200_ln_gate_bwd.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp]
     for which, st in enumerate((SScanFwdParams, SScanBwdParams, SsdFwdParams, SsdBwdParams)):
         if lib.b200_sizeof_params(which) != C.sizeof(st):
             raise RuntimeError(f"libb200ssm ABI mismatch for {st.__name__}: "

@@ -24,8 +24,9 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <typename TZ, typename TO, int NPL>
-__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float* __restrict__ y, const TZ* __restrict__ z, int64_t z_row_stride,
+template <typename TZ, typename TO, int NPL, bool HAS_Z>
+__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float* __restrict__ y, int64_t y_row_stride, const TZ* __restrict__ z,
+                                                                    int64_t z_row_stride,
                                                                     const float* __restrict__ w, const float* __restrict__ b,
                                                                     TO* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
                                                                     int64_t rows, int D, float eps) {
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float*
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int c = lane + 32 * k;
-            v[k] = c < D ? __ldcs(y + r * D + c) : 0.f;
+            v[k] = c < D ? __ldcs(y + r * y_row_stride + c) : 0.f;
             s += v[k];
         }
         const float mu = warp_sum(s) * invD;
@@ -58,16 +59,20 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float*
         for (int k = 0; k < NPL; ++k) {
             const int c = lane + 32 * k;
             if (c < D) {
-                const float zz = ldg_stream(z + r * z_row_stride + c);
                 const float n = (v[k] - mu) * rs * __ldg(w + c) + __ldg(b + c);
-                stg_stream(out + r * D + c, n * zz * sigmoidf_(zz));
+                if constexpr (HAS_Z) {
+                    const float zz = ldg_stream(z + r * z_row_stride + c);
+                    stg_stream(out + r * D + c, n * zz * sigmoidf_(zz));
+                } else {
+                    stg_stream(out + r * D + c, n);
+                }
             }
         }
     }
 }
 
-template <typename TZ, typename TO, int NPL>
-__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __restrict__ dout, const float* __restrict__ y,
+template <typename TZ, typename TO, int NPL, bool HAS_Z>
+__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __restrict__ dout, const float* __restrict__ y, int64_t y_row_stride,
                                                                     const TZ* __restrict__ z, int64_t z_row_stride, const float* __restrict__ w,
                                                                     const float* __restrict__ b, const float* __restrict__ mean,
                                                                     const float* __restrict__ rstd, float* __restrict__ dy, TZ* __restrict__ dz,
@@ -92,15 +97,18 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __
             xh[k] = 0.f;
             g[k] = 0.f;
             if (c < D) {
-                const float yy = __ldcs(y + r * D + c);
-                const float zz = ldg_stream(z + r * z_row_stride + c);
+                const float yy = __ldcs(y + r * y_row_stride + c);
                 const float go = ldg_stream(dout + r * D + c);
-                const float sg = sigmoidf_(zz);
                 const float wc = __ldg(w + c);
                 xh[k] = (yy - mu) * rs;
-                const float n = xh[k] * wc + __ldg(b + c);
-                const float dn = go * zz * sg;
-                stg_stream(dz + r * D + c, go * n * sg * (1.f + zz * (1.f - sg)));
+                float dn = go;
+                if constexpr (HAS_Z) {
+                    const float zz = ldg_stream(z + r * z_row_stride + c);
+                    const float sg = sigmoidf_(zz);
+                    const float n = xh[k] * wc + __ldg(b + c);
+                    dn = go * zz * sg;
+                    stg_stream(dz + r * D + c, go * n * sg * (1.f + zz * (1.f - sg)));
+                }
                 aw[k] += dn * xh[k];
                 ab[k] += dn;
                 g[k] = dn * wc;
@@ -137,17 +145,25 @@ static int lg_grid(int64_t rows) {
 }
 
 template <typename TZ, typename TO, int NPL>
-static int lg_fwd_launch(const void* y, const void* z, int64_t zs, const float* w, const float* b, void* out, float* mean, float* rstd,
+static int lg_fwd_launch(const void* y, int64_t ys, const void* z, int64_t zs, const float* w, const float* b, void* out, float* mean, float* rstd,
                          int64_t rows, int D, float eps, cudaStream_t st) {
-    ln_gate_fwd_kernel<TZ, TO, NPL><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const float*)y, (const TZ*)z, zs, w, b, (TO*)out, mean, rstd, rows, D,
-                                                                             eps);
+    if (z)
+        ln_gate_fwd_kernel<TZ, TO, NPL, true><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const float*)y, ys, (const TZ*)z, zs, w, b, (TO*)out, mean,
+                                                                                       rstd, rows, D, eps);
+    else
+        ln_gate_fwd_kernel<TZ, TO, NPL, false><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const float*)y, ys, (const TZ*)z, zs, w, b, (TO*)out, mean,
+                                                                                        rstd, rows, D, eps);
     return check_launch("ln_gate_fwd_kernel");
 }
 template <typename TZ, typename TO, int NPL>
-static int lg_bwd_launch(const void* dout, const void* y, const void* z, int64_t zs, const float* w, const float* b, const float* mean,
+static int lg_bwd_launch(const void* dout, const void* y, int64_t ys, const void* z, int64_t zs, const float* w, const float* b, const float* mean,
                          const float* rstd, float* dy, void* dz, float* dwp, float* dbp, int64_t rows, int D, cudaStream_t st) {
-    ln_gate_bwd_kernel<TZ, TO, NPL><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const float*)y, (const TZ*)z, zs, w, b, mean, rstd,
-                                                                             dy, (TZ*)dz, dwp, dbp, rows, D);
+    if (z)
+        ln_gate_bwd_kernel<TZ, TO, NPL, true><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const float*)y, ys, (const TZ*)z, zs, w, b,
+                                                                                       mean, rstd, dy, (TZ*)dz, dwp, dbp, rows, D);
+    else
+        ln_gate_bwd_kernel<TZ, TO, NPL, false><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const float*)y, ys, (const TZ*)z, zs, w, b,
+                                                                                        mean, rstd, dy, (TZ*)dz, dwp, dbp, rows, D);
     return check_launch("ln_gate_bwd_kernel");
 }
 
@@ -185,21 +201,24 @@ using namespace b200;
 
 extern "C" int b200_ln_gate_grid(int64_t rows) { return lg_grid(rows); }
 
-extern "C" int b200_ln_gate_fwd(const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w, const float* b,
-                                void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
+extern "C" int b200_ln_gate_fwd(const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
+                                const float* b, void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
                                 b200_stream_t stream) {
-    B200_REQUIRE(y && z && w && b && out && mean && rstd, "b200_ln_gate_fwd: NULL argument");
+    B200_REQUIRE(y && w && b && out && mean && rstd, "b200_ln_gate_fwd: NULL argument");
+    if (!z) z_dtype = out_dtype == B200_BF16 ? B200_BF16 : B200_F32;   // plain LayerNorm: pick an instantiated pair
     B200_REQUIRE(rows >= 0 && D >= 1 && D <= LG_MAXD, "b200_ln_gate_fwd: D = %d outside [1, %d]", D, LG_MAXD);
     if (rows == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    LG_DISPATCH(lg_fwd_launch, y, z, z_row_stride, w, b, out, mean, rstd, rows, D, eps, st);
+    LG_DISPATCH(lg_fwd_launch, y, y_row_stride, z, z_row_stride, w, b, out, mean, rstd, rows, D, eps, st);
 }
 
-extern "C" int b200_ln_gate_bwd(const void* dout, const float* y, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
-                                const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
+extern "C" int b200_ln_gate_bwd(const void* dout, const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype,
+                                const float* w, const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
                                 float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream) {
-    B200_REQUIRE(dout && y && z && w && b && mean && rstd && dy && dz && dw_partial && db_partial, "b200_ln_gate_bwd: NULL argument");
+    B200_REQUIRE(dout && y && w && b && mean && rstd && dy && dw_partial && db_partial, "b200_ln_gate_bwd: NULL argument");
+    B200_REQUIRE((z == nullptr) == (dz == nullptr), "b200_ln_gate_bwd: dz must be given exactly when z is");
+    if (!z) z_dtype = out_dtype == B200_BF16 ? B200_BF16 : B200_F32;
     B200_REQUIRE(rows >= 1 && D >= 1 && D <= LG_MAXD, "b200_ln_gate_bwd: D = %d outside [1, %d]", D, LG_MAXD);
     cudaStream_t st = (cudaStream_t)stream;
-    LG_DISPATCH(lg_bwd_launch, dout, y, z, z_row_stride, w, b, mean, rstd, dy, dz, dw_partial, db_partial, rows, D, st);
+    LG_DISPATCH(lg_bwd_launch, dout, y, y_row_stride, z, z_row_stride, w, b, mean, rstd, dy, dz, dw_partial, db_partial, rows, D, st);
 }

@@ -93,7 +93,12 @@ class SS_Conv_SSM(nn.Module):
 
     def forward(self, input):
         left, right = input.chunk(2, dim=-1)
-        x = self.drop_path(self.self_attention(self.ln_1(right)))
+        if right.is_cuda and right.dtype == torch.float32 and isinstance(self.ln_1, nn.LayerNorm) and right.shape[-1] <= 1024:
+            from .ss2d import layer_norm_rows
+            normed = layer_norm_rows(right, self.ln_1)     # pre-norm, the right half read in place (csrc/lngate.cu)
+        else:
+            normed = self.ln_1(right)
+        x = self.drop_path(self.self_attention(normed))
         left = self.conv33conv33conv11(left.permute(0, 3, 1, 2).contiguous())
         left = left.permute(0, 2, 3, 1)
         out = channel_shuffle(torch.cat((left, x.to(left.dtype)), dim=-1), groups=2)

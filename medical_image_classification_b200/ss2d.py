@@ -67,10 +67,19 @@ class _ProjFn(torch.autograd.Function):
         return dW, dX, None
 
 
+def _rows_view(t, D):
+    """(tensor, row stride) such that row r of the flattened (..., D) tensor starts at data_ptr + r * stride elements;
+    views whose leading dimensions collapse (e.g. one half of a chunk(2, -1)) are used in place."""
+    if t.is_contiguous():
+        return t, D
+    ok = t.dim() >= 2 and t.stride(-1) == 1 and all(t.stride(i) == t.stride(i + 1) * t.shape[i + 1] for i in range(t.dim() - 2))
+    return (t, t.stride(-2)) if ok else (t.contiguous(), D)
+
+
 class LnGateFn(torch.autograd.Function):
-    """out = LayerNorm(y) * silu(z) in one pass over HBM (csrc/lngate.cu) -- reference MedMamba.py:478-479.
-    y (..., D) fp32; z (..., D) fp32 or bf16, only its last dimension has to be contiguous (it is the second half of
-    in_proj's output and is read in place); returns out_dtype (bf16 under autocast = what out_proj casts to)."""
+    """out = LayerNorm(y) [* silu(z)] in one pass over HBM (csrc/lngate.cu) -- reference MedMamba.py:478-479 (with z)
+    and the block pre-norm `ln_1` (MedMamba.py:531, z = None).  y (..., D) fp32, z (..., D) fp32 / bf16; both may be
+    strided views with contiguous rows (halves of a chunk) and are read in place; returns out_dtype."""
 
     @staticmethod
     def forward(ctx, y, z, weight, bias, eps, out_dtype):
@@ -78,30 +87,26 @@ class LnGateFn(torch.autograd.Function):
         _lib.require_cuda(y, z, weight, bias)
         lib = _lib.load()
         D = y.shape[-1]
-        y2 = y.reshape(-1, D)
-        if y2.dtype != torch.float32 or not y2.is_contiguous():
-            y2 = y2.float().contiguous()
-        z2 = z.reshape(-1, D) if z.is_contiguous() else None
-        if z2 is None:   # a strided view with contiguous rows: keep it in place
-            zs = z.stride(-2) if z.dim() >= 2 else D
-            ok = z.stride(-1) == 1 and all(z.stride(i) == z.stride(i + 1) * z.shape[i + 1] for i in range(z.dim() - 2))
-            z2 = z if ok else z.contiguous()
-            zs = zs if ok else D
-        else:
-            zs = D
-        if z2.dtype not in (torch.float32, torch.bfloat16):
-            z2, zs = z2.float().contiguous(), D
-        rows = y2.shape[0]
+        if y.dtype != torch.float32:
+            y = y.float()
+        y2, ys = _rows_view(y, D)
+        z2, zs = (None, 0)
+        if z is not None:
+            if z.dtype not in (torch.float32, torch.bfloat16):
+                z = z.float()
+            z2, zs = _rows_view(z, D)
+        rows = y.numel() // D
         w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
         out = torch.empty((rows, D), dtype=out_dtype, device=y.device)
         mean = torch.empty(rows, dtype=torch.float32, device=y.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=y.device)
+        zcode = _lib.dtype_code(z2.dtype) if z2 is not None else 0
         with torch.cuda.device(y.device):
-            _lib.check(lib.b200_ln_gate_fwd(y2.data_ptr(), z2.data_ptr(), zs, _lib.dtype_code(z2.dtype), w32.data_ptr(), b32.data_ptr(),
-                                            out.data_ptr(), _lib.dtype_code(out_dtype), mean.data_ptr(), rstd.data_ptr(), rows, D, float(eps),
+            _lib.check(lib.b200_ln_gate_fwd(y2.data_ptr(), ys, _lib.ptr(z2), zs, zcode, w32.data_ptr(), b32.data_ptr(), out.data_ptr(),
+                                            _lib.dtype_code(out_dtype), mean.data_ptr(), rstd.data_ptr(), rows, D, float(eps),
                                             _lib.stream_ptr(y.device)), "b200_ln_gate_fwd")
         ctx.save_for_backward(y2, z2, w32, b32, mean, rstd)
-        ctx.zs, ctx.shape, ctx.zshape = zs, y.shape, z.shape
+        ctx.ys, ctx.zs, ctx.shape, ctx.zshape, ctx.rows = ys, zs, y.shape, (z.shape if z is not None else None), rows
         ctx.wdtype, ctx.bdtype = weight.dtype, bias.dtype
         return out.view(*y.shape[:-1], D)
 
@@ -110,19 +115,21 @@ class LnGateFn(torch.autograd.Function):
         from . import _lib
         lib = _lib.load()
         y2, z2, w32, b32, mean, rstd = ctx.saved_tensors
-        rows, D = y2.shape
+        rows, D = ctx.rows, ctx.shape[-1]
         dout = dout.reshape(rows, D).contiguous()
-        dy = torch.empty_like(y2)
-        dz = torch.empty((rows, D), dtype=z2.dtype, device=y2.device)
+        dev = dout.device
+        dy = torch.empty((rows, D), dtype=torch.float32, device=dev)
+        dz = torch.empty((rows, D), dtype=z2.dtype, device=dev) if z2 is not None else None
         grid = lib.b200_ln_gate_grid(rows)
-        part = torch.empty((2, grid, D), dtype=torch.float32, device=y2.device)
-        with torch.cuda.device(y2.device):
-            _lib.check(lib.b200_ln_gate_bwd(dout.data_ptr(), y2.data_ptr(), z2.data_ptr(), ctx.zs, _lib.dtype_code(z2.dtype), w32.data_ptr(),
-                                            b32.data_ptr(), _lib.dtype_code(dout.dtype), mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(),
-                                            dz.data_ptr(), part[0].data_ptr(), part[1].data_ptr(), rows, D, _lib.stream_ptr(y2.device)),
-                       "b200_ln_gate_bwd")
+        part = torch.empty((2, grid, D), dtype=torch.float32, device=dev)
+        zcode = _lib.dtype_code(z2.dtype) if z2 is not None else 0
+        with torch.cuda.device(dev):
+            _lib.check(lib.b200_ln_gate_bwd(dout.data_ptr(), y2.data_ptr(), ctx.ys, _lib.ptr(z2), ctx.zs, zcode, w32.data_ptr(), b32.data_ptr(),
+                                            _lib.dtype_code(dout.dtype), mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(), _lib.ptr(dz),
+                                            part[0].data_ptr(), part[1].data_ptr(), rows, D, _lib.stream_ptr(dev)), "b200_ln_gate_bwd")
         dwb = part.sum(1)
-        return dy.view(ctx.shape), dz.view(ctx.zshape), dwb[0].to(ctx.wdtype), dwb[1].to(ctx.bdtype), None, None
+        return (dy.view(ctx.shape), dz.view(ctx.zshape) if dz is not None else None, dwb[0].to(ctx.wdtype), dwb[1].to(ctx.bdtype),
+                None, None)
 
 
 class DwConvSiluFn(torch.autograd.Function):
@@ -168,10 +175,18 @@ class DwConvSiluFn(torch.autograd.Function):
         return dxin, dweight, dbias
 
 
+def _autocast_out_dtype():
+    return torch.bfloat16 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else torch.float32
+
+
 def ln_gate(y, z, norm: nn.LayerNorm):
-    """LayerNorm(y) * silu(z) through libb200ssm (CUDA only)."""
-    out_dtype = torch.bfloat16 if (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16) else torch.float32
-    return LnGateFn.apply(y, z, norm.weight, norm.bias, norm.eps, out_dtype)
+    """LayerNorm(y) * silu(z) through libb200ssm (CUDA only); bf16 out under autocast (= what the next Linear casts to)."""
+    return LnGateFn.apply(y, z, norm.weight, norm.bias, norm.eps, _autocast_out_dtype())
+
+
+def layer_norm_rows(y, norm: nn.LayerNorm):
+    """Plain LayerNorm over the last dimension of a (possibly strided) fp32 tensor through libb200ssm."""
+    return LnGateFn.apply(y, None, norm.weight, norm.bias, norm.eps, _autocast_out_dtype())
 
 
 class SS2D(nn.Module):

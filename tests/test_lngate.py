@@ -62,3 +62,28 @@ def test_ln_gate_full_size_properties():
     assert torch.equal(out[:1], out2)
     shifted = LnGateFn.apply(y + 3.0, z, w, b, 1e-5, torch.float32)
     assert relerr(shifted, out) < 1e-5
+
+
+@pytest.mark.parametrize("D", [48, 96, 384])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_plain_layer_norm_on_strided_half(D, odt):
+    """z = None: the block pre-norm (MedMamba.py:531) on the right half of the block input, read in place."""
+    from medical_image_classification_b200.ss2d import LnGateFn
+    dev = "cuda"
+    torch.manual_seed(D + 1)
+    inp = (1.5 * torch.randn(2, 9, 10, 2 * D, device=dev) - 0.3).requires_grad_()
+    right = inp.chunk(2, dim=-1)[1]
+    w = (1.0 + 0.1 * torch.randn(D, device=dev)).requires_grad_()
+    b = (0.1 * torch.randn(D, device=dev)).requires_grad_()
+    out = LnGateFn.apply(right, None, w, b, 1e-6, odt)
+    g = torch.randn_like(out)
+    out.backward(g)
+    got = [t.grad.clone() for t in (inp, w, b)]
+    for t in (inp, w, b):
+        t.grad = None
+    o2 = torch.nn.functional.layer_norm(inp.chunk(2, dim=-1)[1], (D,), w, b, 1e-6)
+    o2.backward(g.float())
+    ftol, btol = (2e-6, 2e-5) if odt == torch.float32 else (4e-3, 1e-2)
+    assert relerr(out, o2) < ftol
+    for name, a, c in zip(("dinput", "dw", "db"), got, (inp.grad, w.grad, b.grad)):
+        assert relerr(a, c) < btol, name
