@@ -79,6 +79,7 @@ EXPORTS = [
     "b200_rmsnorm_gated_fwd", "b200_rmsnorm_gated_bwd",
     "b200_ln_gate_grid", "b200_ln_gate_fwd", "b200_ln_gate_bwd",
     "b200_dwconv_silu_fwd", "b200_dwconv_silu_bwd",
+    "b200_shuffle_cat_add_fwd", "b200_shuffle_cat_add_bwd",
     "b200_last_error", "b200_version", "b200_kernel_launches", "b200_sizeof_params",
 ]
 
@@ -120,6 +121,8 @@ def load() -> C.CDLL:
     lib.b200_rmsnorm_gated_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]
     lib.b200_dwconv_silu_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_dwconv_silu_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.b200_shuffle_cat_add_fwd.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, vp]
+    lib.b200_shuffle_cat_add_bwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_ln_gate_grid.argtypes = [i64]
     lib.b200_ln_gate_fwd.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]
     lib.b200_ln_gate_bwd.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp]

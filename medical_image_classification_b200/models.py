@@ -68,6 +68,38 @@ def channel_shuffle(x, groups: int):
     return x.view(B, H, W, groups, C // groups).transpose(3, 4).reshape(B, H, W, C)
 
 
+class ShuffleCatAddFn(torch.autograd.Function):
+    """out (B, H, W, 2c) fp32 = channel_shuffle(cat(left^T, x), 2) + input with left (B, c, H, W) planes and x
+    (B, H, W, c) channels-last (csrc/glue.cu) -- reference MedMamba.py:486-499, 533-538."""
+
+    @staticmethod
+    def forward(ctx, left, x, inp):
+        from . import _lib
+        _lib.require_cuda(left, x, inp)
+        lib = _lib.load()
+        B, c, H, W = left.shape
+        left, x, inp = left.contiguous(), x.to(left.dtype).contiguous(), inp.contiguous()
+        out = torch.empty((B, H, W, 2 * c), dtype=torch.float32, device=inp.device)
+        with torch.cuda.device(inp.device):
+            _lib.check(lib.b200_shuffle_cat_add_fwd(left.data_ptr(), x.data_ptr(), _lib.dtype_code(left.dtype), inp.data_ptr(), out.data_ptr(),
+                                                    B, c, H * W, _lib.stream_ptr(inp.device)), "b200_shuffle_cat_add_fwd")
+        ctx.meta = (B, c, H, W, left.dtype, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import _lib
+        lib = _lib.load()
+        B, c, H, W, ldt, xdt = ctx.meta
+        dout = dout.float().contiguous()
+        dleft = torch.empty((B, c, H, W), dtype=ldt, device=dout.device)
+        dx = torch.empty((B, H, W, c), dtype=ldt, device=dout.device)
+        with torch.cuda.device(dout.device):
+            _lib.check(lib.b200_shuffle_cat_add_bwd(dout.data_ptr(), dleft.data_ptr(), dx.data_ptr(), _lib.dtype_code(ldt), B, c, H * W,
+                                                    _lib.stream_ptr(dout.device)), "b200_shuffle_cat_add_bwd")
+        return dleft, dx, dout
+
+
 class SS_Conv_SSM(nn.Module):
     """Two-branch block: half the channels through conv3x3-conv3x3-conv1x1, half through
     LayerNorm -> SS2D; concat, channel shuffle, residual."""
@@ -100,6 +132,9 @@ class SS_Conv_SSM(nn.Module):
             normed = self.ln_1(right)
         x = self.drop_path(self.self_attention(normed))
         left = self.conv33conv33conv11(left.permute(0, 3, 1, 2).contiguous())
+        if (input.is_cuda and input.dtype == torch.float32 and left.dtype in (torch.float32, torch.bfloat16)
+                and x.dtype in (torch.float32, torch.bfloat16) and left.shape[0] <= 65535):
+            return ShuffleCatAddFn.apply(left, x, input)   # cat + channel shuffle + residual in one pass (csrc/glue.cu)
         left = left.permute(0, 2, 3, 1)
         out = channel_shuffle(torch.cat((left, x.to(left.dtype)), dim=-1), groups=2)
         return out + input
