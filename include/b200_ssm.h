@@ -254,15 +254,16 @@ int b200_dwconv_silu_bwd(const float* gout, const void* xin, int64_t pix_stride,
 /* ------------------------------------------------------------------------------------------
  * Block tail: out = channel_shuffle(cat(left, x), groups = 2) + input -- replaces the
  * permute / cat / shuffle copy / residual add of SS_Conv_SSM.forward (reference MedMamba.py:486-499, 533-538).
- *   left (B, c, P) planes (the conv branch, P = H*W) and x (B, P, c) channels-last (the SS2D branch), both lx_dtype
+ *   left (B, c, P) planes, or (B, P, c) when left_channels_last (the conv branch run in torch.channels_last; P = H*W),
+ *   and x (B, P, c) channels-last (the SS2D branch), both lx_dtype
  *   in {F32, BF16}; input, out (B, P, 2 c) f32.  out[b,p,2j] = left[b,j,p] + input[b,p,2j];
  *   out[b,p,2j+1] = x[b,p,j] + input[b,p,2j+1].  Backward: dout (B, P, 2 c) f32 -> dleft (B, c, P), dx (B, P, c)
  *   in lx_dtype (the gradient of `input` is dout itself).
  * ------------------------------------------------------------------------------------------ */
-int b200_shuffle_cat_add_fwd(const void* left, const void* x, int32_t lx_dtype, const float* input, float* out, int32_t B, int32_t c,
-                             int32_t P, b200_stream_t stream);
-int b200_shuffle_cat_add_bwd(const float* dout, void* dleft, void* dx, int32_t lx_dtype, int32_t B, int32_t c, int32_t P,
-                             b200_stream_t stream);
+int b200_shuffle_cat_add_fwd(const void* left, int32_t left_channels_last, const void* x, int32_t lx_dtype, const float* input,
+                             float* out, int32_t B, int32_t c, int32_t P, b200_stream_t stream);
+int b200_shuffle_cat_add_bwd(const float* dout, void* dleft, int32_t left_channels_last, void* dx, int32_t lx_dtype, int32_t B,
+                             int32_t c, int32_t P, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 const char* b200_last_error(void);   /* thread-local message of the last failing call */

@@ -25,15 +25,25 @@ import torch.nn.functional as F
 from . import _lib
 
 # 0: fp32-accurate tensor-core products (3xTF32 split, default); 1: single-pass TF32 (the arithmetic
-# of the reference's Triton kernels on fp32 inputs)
+# of the reference's Triton kernels on fp32 inputs: tl.dot with its default allow_tf32).  Under bf16 autocast --
+# BASELINE.json configs[2], where everything around the operator is bf16 -- the single-pass mode is used unless
+# set_precision() was called explicitly: it is exactly the reference's own arithmetic for this call.
 _precision = 0
+_explicit = False
+
+
+def _effective_precision() -> int:
+    if not _explicit and torch.is_autocast_enabled():
+        return 1
+    return _precision
 
 
 def set_precision(mode: int) -> None:
-    global _precision
+    global _precision, _explicit
     if mode not in (0, 1):
         raise ValueError("precision must be 0 (3xTF32, fp32-accurate) or 1 (single-pass TF32)")
     _precision = mode
+    _explicit = True
 
 
 def _fill_fwd(p, x, dt, A, Bm, Cm, D, dt_bias, chunk_size, dt_softplus, dt_limit, initial_states, precision):
@@ -69,13 +79,14 @@ class SsdChunkScanFn(torch.autograd.Function):
         nbytes = lib.b200_ssd_workspace_bytes(batch, L, H, P, G, N, chunk_size)
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
         p = _lib.SsdFwdParams()
-        _fill_fwd(p, x, dt_, A32, B_, C_, D32, bias32, chunk_size, dt_softplus, dt_limit, init32, _precision)
+        prec = _effective_precision()
+        _fill_fwd(p, x, dt_, A32, B_, C_, D32, bias32, chunk_size, dt_softplus, dt_limit, init32, prec)
         p.out_stride[:] = list(out.stride())
         p.out, p.final_states, p.workspace = out.data_ptr(), _lib.ptr(fin), ws.data_ptr()
         with torch.cuda.device(dev):
             _lib.check(lib.b200_ssd_fwd(ctypes.byref(p), _lib.stream_ptr(dev)), "b200_ssd_fwd")
         ctx.save_for_backward(x, dt_, A32, B_, C_, D32, bias32, init32, out, ws)
-        ctx.cfg = (chunk_size, bool(dt_softplus), tuple(dt_limit), _precision)
+        ctx.cfg = (chunk_size, bool(dt_softplus), tuple(dt_limit), prec)
         ctx.dtypes = (dt.dtype, A.dtype, B.dtype, C.dtype, None if D is None else D.dtype,
                       None if dt_bias is None else dt_bias.dtype)
         if return_final_states:

@@ -16,12 +16,16 @@ def ref(left, x, inp):
 
 @pytest.mark.parametrize("shape", [(2, 48, 56, 56), (3, 96, 28, 28), (2, 384, 7, 7), (1, 20, 5, 9), (2, 33, 3, 2)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_shuffle_cat_add_bit_exact(shape, dtype):
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_shuffle_cat_add_bit_exact(shape, dtype, channels_last):
     from medical_image_classification_b200.models import ShuffleCatAddFn
     B, c, H, W = shape
     dev = "cuda"
     torch.manual_seed(c)
-    left = torch.randn(B, c, H, W, device=dev, dtype=dtype).requires_grad_()
+    left = torch.randn(B, c, H, W, device=dev, dtype=dtype)
+    if channels_last:
+        left = left.contiguous(memory_format=torch.channels_last)
+    left.requires_grad_()
     x = torch.randn(B, H, W, c, device=dev, dtype=dtype).requires_grad_()
     inp = torch.randn(B, H, W, 2 * c, device=dev).requires_grad_()
     out = ShuffleCatAddFn.apply(left, x, inp)
