@@ -187,10 +187,42 @@ def medssd_case(seed=0):
     print("wrote medssd_tiny loss", float(loss))
 
 
+def crossmamba_case(name, d_model, d_state, headdim, H, W, batch, seed=0):
+    """Reference CrossMamba (CrossMamba/CrossMamba_fusion_2b2.py:54-388): two inputs, x from each branch, B/C/dt from the
+    mixed tensors; SSD operator = oracle stand-in (module data flow pinned, operator PARITY UNPINNED)."""
+    cm = ref_import.load_crossmamba()
+    torch.manual_seed(seed)
+    m = cm.CrossMamba(d_model=d_model, d_state=d_state, headdim=headdim, chunk_size=32)
+    with torch.no_grad():
+        m.Ds.add_(0.5 * torch.randn_like(m.Ds))
+        m.A_logs.add_(0.3 * torch.randn_like(m.A_logs))
+        m.dt_bias.add_(0.3 * torch.randn_like(m.dt_bias))
+        m.norm.weight.add_(0.2 * torch.randn_like(m.norm.weight))
+    ins = [torch.randn(batch, H, W, d_model, requires_grad=True) for _ in range(4)]   # u1, u2, u2_cat_u1, u1_cat_u2
+    g1, g2 = torch.randn(batch, H, W, d_model), torch.randn(batch, H, W, d_model)
+    o1, o2 = m(*ins)
+    (o1 * g1).sum().add((o2 * g2).sum()).backward()
+    rec = {"g1": _np(g1), "g2": _np(g2), "out1": _np(o1), "out2": _np(o2),
+           "cfg": np.array([d_model, d_state, headdim, H, W, batch])}
+    for i, t in enumerate(ins):
+        rec[f"in{i}"] = _np(t)
+        rec[f"din{i}"] = _np(t.grad)
+    for k, v in m.state_dict().items():
+        rec["sd." + k] = _np(v)
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            rec["grad." + k] = _np(p.grad)
+    np.savez_compressed(os.path.join(OUT, f"crossmamba_{name}.npz"), **rec)
+    print("wrote crossmamba", name, float(o1.abs().max()), float(o2.abs().max()))
+
+
 def main():
     assert ref_import.available(), "/root/reference is not mounted"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--crossmamba-only" in sys.argv:
+        crossmamba_case("d32_6x5", 32, 8, 16, 6, 5, 2)
+        return
     if "--ssd-only" in sys.argv:
         ss2d_ssd_case("d32_7x5", 32, 8, 16, 7, 5, 2)
         ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
@@ -213,6 +245,7 @@ def main():
     ss2d_ssd_case("d32_7x5", 32, 8, 16, 7, 5, 2)
     ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
     medssd_case()
+    crossmamba_case("d32_6x5", 32, 8, 16, 6, 5, 2)
 
 
 if __name__ == "__main__":

@@ -135,7 +135,7 @@ def _oracle_ssd_fn():
     return mamba_chunk_scan_combined
 
 
-def load_medssd():
+def load_medssd(rel_path: str = "SSD/MedSSD.py", name: str = "ref_MedSSD"):
     """Reference SSD/MedSSD.py with mamba_ssm's pieces replaced by CPU stand-ins: the SSD operator by the oracle,
     the gated RMSNorm by its published formula y = rmsnorm(x * silu(z)) * w (norm_before_gate=False)."""
     import torch
@@ -176,7 +176,7 @@ def load_medssd():
         hub.PyTorchModelHubMixin = type("PyTorchModelHubMixin", (), {})
         sys.modules["huggingface_hub"] = hub
     try:
-        mod = _load("ref_MedSSD", os.path.join(REF_ROOT, "SSD/MedSSD.py"))
+        mod = _load(name, os.path.join(REF_ROOT, rel_path))
     finally:
         for k, v in saved.items():
             if v is None:
@@ -184,3 +184,9 @@ def load_medssd():
             else:
                 sys.modules[k] = v
     return mod
+
+
+def load_crossmamba():
+    """Reference CrossMamba/CrossMamba_fusion_2b2.py (two-branch CrossMamba module, :54-388) with the same CPU stand-ins
+    as load_medssd (oracle SSD operator, formula RMSNorm)."""
+    return load_medssd("CrossMamba/CrossMamba_fusion_2b2.py", "ref_CrossMamba")

@@ -210,3 +210,33 @@ def test_medssd_tiny_matches_reference():
             assert rel(p.grad, g["grad." + k]) < 2e-3, k
             checked += 1
     assert checked > 10
+
+
+CROSS_CASES = sorted(glob.glob(os.path.join(GOLDEN, "crossmamba_*.npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", CROSS_CASES, ids=[os.path.basename(p)[:-4] for p in CROSS_CASES])
+def test_crossmamba_module_matches_reference(path):
+    """The two-branch CrossMamba mixer (reference CrossMamba/CrossMamba_fusion_2b2.py:54-388)
+    with the reference's state_dict: both outputs, all four input gradients and every parameter gradient."""
+    from medical_image_classification_b200.crossmamba import CrossMamba
+    g = np.load(path)
+    d_model, d_state, headdim, H, W, batch = (int(v) for v in g["cfg"])
+    m = CrossMamba(d_model=d_model, d_state=d_state, headdim=headdim, chunk_size=32)
+    m.load_state_dict({k[3:]: torch.tensor(g[k]) for k in g.files if k.startswith("sd.")}, strict=True)
+    m = m.cuda()
+    ins = [torch.tensor(g[f"in{i}"]).cuda().requires_grad_() for i in range(4)]
+    o1, o2 = m(*ins)
+    assert rel(o1, g["out1"]) < 2e-5 and rel(o2, g["out2"]) < 2e-5
+    ((o1 * torch.tensor(g["g1"]).cuda()).sum() + (o2 * torch.tensor(g["g2"]).cuda()).sum()).backward()
+    for i, t in enumerate(ins):
+        assert rel(t.grad, g[f"din{i}"]) < 1e-4, i
+    checked = 0
+    for k, p in m.named_parameters():
+        if "grad." + k in g.files:
+            assert rel(p.grad, g["grad." + k]) < 2e-4, k
+            checked += 1
+        else:
+            assert p.grad is None, k        # in_proj / conv2d: present in the state_dict, unused by the forward
+    assert checked >= 10
