@@ -76,7 +76,11 @@ class SS2D_with_SSD(nn.Module):
         d_mlp = (zxbcdt.shape[-1] - 2 * self.d_ssm - 2 * self.ngroups * self.d_state - self.nheads) // 2
         z0, x0, z, xBCdt = torch.split(
             zxbcdt, [d_mlp, d_mlp, self.d_ssm, self.d_ssm + 2 * self.ngroups * self.d_state + self.nheads], dim=-1)
-        xBCdt = self.act(self.conv2d(xBCdt.permute(0, 3, 1, 2).contiguous()))           # (B, c, H, W)
+        if xBCdt.is_cuda and self.d_conv == 3 and W <= 64 and xBCdt.dtype in (torch.float32, torch.bfloat16):
+            from .ss2d import DwConvSiluFn                                              # conv3x3 + SiLU, channels-last slice in place -> fp32 planes
+            xBCdt = DwConvSiluFn.apply(xBCdt, self.conv2d.weight, self.conv2d.bias)    # (B, c, H, W)
+        else:
+            xBCdt = self.act(self.conv2d(xBCdt.permute(0, 3, 1, 2).contiguous()))       # (B, c, H, W)
 
         # cross-scan of x, B, C and dt together (SSD/MedSSD.py:332-336)
         hwwh = torch.stack([xBCdt.reshape(B, -1, L), xBCdt.transpose(2, 3).reshape(B, -1, L)], dim=1)
