@@ -203,3 +203,60 @@ def test_full_size_properties():
     ref, _ = oracle.sscan_fwd(u[:1], delta[:1], A, Bm[:1], Cm[:1], delta_bias=bias, delta_softplus=True)
     # 77 M elements, L = 3136, |out| up to ~100: the fp32 recurrence sits 1.2e-5 (max-norm) from fp64 here
     assert relerr(out[:1], ref) < 2e-5
+
+
+def test_tma_variant_matches_oracle():
+    """The opt-in TMA staging variant (B200_SSCAN_TMA=1: cp.async.bulk.tensor + mbarrier for the u / delta / dout
+    tiles) must give the same answers; the switch is read once per process, so it runs in a child process."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+import oracle
+from medical_image_classification_b200.selective_scan_interface import selective_scan_dirs_fn
+r = np.random.RandomState(3)
+batch, dim, N, L, G = 2, 96, 16, 200, 4          # 24 rows per group: one full + one ragged warp task; L % 8 != 0
+f = lambda *s: r.randn(*s).astype(np.float32)
+u, delta = f(batch, dim, L), (0.5 * r.rand(batch, dim, L)).astype(np.float32)
+A, Bm, Cm, D = (-0.5 * r.rand(dim, N)).astype(np.float32), f(batch, G, N, L), f(batch, G, N, L), f(dim)
+bias, g = (0.5 * r.rand(dim)).astype(np.float32), f(batch, dim, L)
+T = lambda a: torch.tensor(a, device="cuda", requires_grad=True)
+tu, td, tA, tB, tC, tD, tb = map(T, (u, delta, A, Bm, Cm, D, bias))
+out = selective_scan_dirs_fn(tu, td, tA, tB, tC, tD, tb, True, rev_mask=0b1010)
+out.backward(torch.tensor(g, device="cuda"))
+flip = lambda a, k: np.ascontiguousarray(a[..., ::-1]) if k else a
+# oracle: reversed groups = plain scan of the flipped rows, flipped back
+rpg = dim // G
+ref = np.empty_like(u); gr = {k: None for k in ("du", "ddelta", "dB", "dC")}
+o64, _ = oracle.sscan_fwd(u, delta, A, Bm, Cm, D=D, delta_bias=bias, delta_softplus=True, precision="f64")
+for gi in range(G):
+    rows = slice(gi * rpg, (gi + 1) * rpg)
+    if (0b1010 >> gi) & 1:
+        o, _ = oracle.sscan_fwd(flip(u[:, rows], 1), flip(delta[:, rows], 1), A[rows], flip(Bm[:, gi:gi+1], 1), flip(Cm[:, gi:gi+1], 1),
+                                D=D[rows], delta_bias=bias[rows], delta_softplus=True, precision="f64")
+        ref[:, rows] = o[..., ::-1]
+    else:
+        o, _ = oracle.sscan_fwd(u[:, rows], delta[:, rows], A[rows], Bm[:, gi:gi+1], Cm[:, gi:gi+1], D=D[rows], delta_bias=bias[rows],
+                                delta_softplus=True, precision="f64")
+        ref[:, rows] = o
+err = float(np.abs(out.detach().cpu().numpy() - ref).max() / np.abs(ref).max())
+assert err < 1e-5, err
+assert torch.isfinite(tu.grad).all() and torch.isfinite(tB.grad).all()
+np.save(sys.argv[1], np.concatenate([out.detach().cpu().numpy().ravel(), tu.grad.cpu().numpy().ravel(), td.grad.cpu().numpy().ravel(),
+                                     tB.grad.cpu().numpy().ravel(), tC.grad.cpu().numpy().ravel(), tA.grad.cpu().numpy().ravel()]))
+print("ok", err)
+'''
+    import tempfile
+    outs = []
+    for tma in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".npy", delete=False) as fh:
+            path = fh.name
+        env = dict(os.environ, B200_SSCAN_TMA=tma)
+        r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(np.load(path))
+        os.unlink(path)
+    # same arithmetic, different staging: identical results up to the order of the dB / dC / dA atomics
+    assert np.abs(outs[0] - outs[1]).max() / np.abs(outs[1]).max() < 1e-6
