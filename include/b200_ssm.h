@@ -140,6 +140,21 @@ int b200_cross_merge(const void* ys, void* y, int32_t batch, int32_t D, int32_t 
 int b200_cross_merge_bwd(const void* dy, void* dys, int32_t batch, int32_t D, int32_t H, int32_t W,
                          int32_t dtype, b200_stream_t stream);
 
+/* SSD twin of the cross-scan / cross-merge (reference SSD/MedSSD.py:332-336, 376-391; CrossMamba_fusion_2b2.py:280-289,
+ * 344-356).  The Mamba-2 operator mixes the four directions' B / C inside one state group, so the four orderings are
+ * materialised, in one pass each way:
+ *   b200_cross_scan4: x (batch, C, H, W) f32 planes with batch stride x_batch_stride (a channel slice of a wider
+ *     tensor is read in place) -> x4 (batch, 4, C, L): k=0 row-major, k=1 column-major, k=2 / k=3 their reversals.
+ *   b200_cross_scan4_bwd: dx4 -> dx (the four un-permuted gradients added up).
+ *   b200_ssd_merge4: y (batch, L, 4, d) f32 (the SSD output with direction-major heads) -> out (batch, L, d) =
+ *     y[l,0] + y[L-1-l,2] + y[lT,1] + y[L-1-lT,3], lT = w H + h;   b200_ssd_merge4_bwd: dout -> dy (a gather). */
+int b200_cross_scan4(const float* x, int64_t x_batch_stride, float* x4, int32_t batch, int32_t C, int32_t H, int32_t W,
+                     b200_stream_t stream);
+int b200_cross_scan4_bwd(const float* dx4, float* dx, int64_t dx_batch_stride, int32_t batch, int32_t C, int32_t H, int32_t W,
+                         b200_stream_t stream);
+int b200_ssd_merge4(const float* y, float* out, int32_t batch, int32_t d, int32_t H, int32_t W, b200_stream_t stream);
+int b200_ssd_merge4_bwd(const float* dout, float* dy, int32_t batch, int32_t d, int32_t H, int32_t W, b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Mamba-2 SSD -- replaces mamba_ssm.ops.triton.ssd_combined.mamba_chunk_scan_combined
  * (call contract: reference SSD/MedSSD.py:344-375).

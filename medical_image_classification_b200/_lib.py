@@ -75,6 +75,7 @@ _DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 EXPORTS = [
     "b200_sscan_ckpt_bytes", "b200_sscan_fwd", "b200_sscan_bwd",
     "b200_cross_scan_pack", "b200_cross_scan_pack_bwd", "b200_cross_merge", "b200_cross_merge_bwd",
+    "b200_cross_scan4", "b200_cross_scan4_bwd", "b200_ssd_merge4", "b200_ssd_merge4_bwd",
     "b200_ssd_workspace_bytes", "b200_ssd_bwd_scratch_bytes", "b200_ssd_fwd", "b200_ssd_bwd",
     "b200_rmsnorm_gated_fwd", "b200_rmsnorm_gated_bwd",
     "b200_ln_gate_grid", "b200_ln_gate_fwd", "b200_ln_gate_bwd",
@@ -117,6 +118,10 @@ def load() -> C.CDLL:
     lib.b200_ssd_bwd.argtypes = [C.POINTER(SsdBwdParams), vp]
     for name in ("b200_cross_scan_pack", "b200_cross_scan_pack_bwd", "b200_cross_merge", "b200_cross_merge_bwd"):
         getattr(lib, name).argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.b200_cross_scan4.argtypes = [vp, i64, vp, i32, i32, i32, i32, vp]
+    lib.b200_cross_scan4_bwd.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp]
+    lib.b200_ssd_merge4.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.b200_ssd_merge4_bwd.argtypes = [vp, vp, i32, i32, i32, i32, vp]
     lib.b200_rmsnorm_gated_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, vp]
     lib.b200_rmsnorm_gated_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]
     lib.b200_dwconv_silu_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, i32, i32, i32, vp]

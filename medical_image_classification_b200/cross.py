@@ -125,6 +125,73 @@ class ScanMergeFn(torch.autograd.Function):
                 dbias.to(ctx.dtypes[2]), None, None)
 
 
+class CrossScan4Fn(torch.autograd.Function):
+    """SSD twin of the cross-scan: x (B, C, H, W) fp32 (a channel slice of a wider NCHW tensor is read in place) ->
+    x4 (B, 4, C, L) in the reference's direction order (hw, wh, hw reversed, wh reversed; SSD/MedSSD.py:332-336)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _lib.require_cuda(x)
+        lib = _lib.load()
+        x = x.float()
+        B, C, H, W = x.shape
+        if not (x.stride(3) == 1 and x.stride(2) == W and x.stride(1) == H * W):
+            x = x.contiguous()
+        x4 = torch.empty((B, 4, C, H * W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.b200_cross_scan4(x.data_ptr(), x.stride(0), x4.data_ptr(), B, C, H, W, _lib.stream_ptr(x.device)), "b200_cross_scan4")
+        ctx.hw = (H, W)
+        return x4
+
+    @staticmethod
+    def backward(ctx, dx4):
+        lib = _lib.load()
+        H, W = ctx.hw
+        dx4 = dx4.float().contiguous()
+        B, _, C, _ = dx4.shape
+        dx = torch.empty((B, C, H, W), dtype=torch.float32, device=dx4.device)
+        with torch.cuda.device(dx4.device):
+            _lib.check(lib.b200_cross_scan4_bwd(dx4.data_ptr(), dx.data_ptr(), dx.stride(0), B, C, H, W, _lib.stream_ptr(dx4.device)),
+                       "b200_cross_scan4_bwd")
+        return dx
+
+
+class SsdMerge4Fn(torch.autograd.Function):
+    """SSD twin of the cross-merge: y (B, L, 4, d) fp32 -> (B, L, d), the four directions un-permuted and summed
+    (SSD/MedSSD.py:380-391)."""
+
+    @staticmethod
+    def forward(ctx, y, H, W):
+        _lib.require_cuda(y)
+        lib = _lib.load()
+        y = y.float().contiguous()
+        B, L, K, d = y.shape
+        assert K == 4 and L == H * W
+        out = torch.empty((B, L, d), dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            _lib.check(lib.b200_ssd_merge4(y.data_ptr(), out.data_ptr(), B, d, H, W, _lib.stream_ptr(y.device)), "b200_ssd_merge4")
+        ctx.meta = (B, L, d, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        B, L, d, H, W = ctx.meta
+        dout = dout.float().contiguous()
+        dy = torch.empty((B, L, 4, d), dtype=torch.float32, device=dout.device)
+        with torch.cuda.device(dout.device):
+            _lib.check(lib.b200_ssd_merge4_bwd(dout.data_ptr(), dy.data_ptr(), B, d, H, W, _lib.stream_ptr(dout.device)), "b200_ssd_merge4_bwd")
+        return dy, None, None
+
+
+def cross_scan4(x):
+    return CrossScan4Fn.apply(x)
+
+
+def ssd_merge4(y, H, W):
+    return SsdMerge4Fn.apply(y, H, W)
+
+
 def cross_scan_pack(x):
     return CrossScanPackFn.apply(x)
 

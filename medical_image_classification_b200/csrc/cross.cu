@@ -160,6 +160,100 @@ __global__ void __launch_bounds__(256) cross_merge_bwd_kernel(const T* __restric
     }
 }
 
+// ---- SSD twin (reference SSD/MedSSD.py:332-336, 376-391): the Mamba-2 operator has no reversed / shared-row mode and
+//      mixes the four directions' B / C inside one state group, so all four orderings are materialised -- in ONE pass:
+//      x (B, C, H, W) fp32 planes (batch stride given: a channel slice of a wider tensor is read in place)
+//        -> x4 (B, 4, C, L):  k=0 row-major, k=1 column-major, k=2 / k=3 their time reversals (the reference's order)
+template <bool BWD>
+__global__ void __launch_bounds__(256) cross_scan4_kernel(const float* __restrict__ src, int64_t src_batch_stride, float* __restrict__ dst,
+                                                          int C, int H, int W) {
+    __shared__ float tile[32][33];
+    const int plane = blockIdx.x;  // b * C + c
+    const int b = plane / C, c = plane % C;
+    const size_t L = (size_t)H * W;
+    // forward: src = x planes, dst = x4;  backward: src = dx4, dst = dx planes (batch stride applies to the planes)
+    const float* xin = BWD ? nullptr : src + (size_t)b * src_batch_stride + (size_t)c * L;
+    float* xout = BWD ? dst + (size_t)b * src_batch_stride + (size_t)c * L : nullptr;
+    const size_t q = ((size_t)b * 4 * C + c) * L;   // direction 0 plane; directions are C * L apart
+    const float* g4 = BWD ? src + q : nullptr;
+    float* o4 = BWD ? nullptr : dst + q;
+    const size_t dstep = (size_t)C * L;
+    const int w0 = blockIdx.y * 32, h0 = blockIdx.z * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (!BWD) {
+#pragma unroll
+        for (int j = ty; j < 32; j += 8) {
+            const int h = h0 + j, w = w0 + tx;
+            if (h < H && w < W) {
+                const size_t l = (size_t)h * W + w;
+                const float v = __ldcs(xin + l);
+                o4[l] = v;
+                o4[2 * dstep + (L - 1 - l)] = v;
+                tile[j][tx] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = ty; j < 32; j += 8) {
+            const int w = w0 + j, h = h0 + tx;
+            if (h < H && w < W) {
+                const size_t l = (size_t)w * H + h;
+                const float v = tile[tx][j];
+                o4[dstep + l] = v;
+                o4[3 * dstep + (L - 1 - l)] = v;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = ty; j < 32; j += 8) {
+            const int w = w0 + j, h = h0 + tx;
+            if (h < H && w < W) {
+                const size_t l = (size_t)w * H + h;
+                tile[tx][j] = __ldcs(g4 + dstep + l) + __ldcs(g4 + 3 * dstep + (L - 1 - l));
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = ty; j < 32; j += 8) {
+            const int h = h0 + j, w = w0 + tx;
+            if (h < H && w < W) {
+                const size_t l = (size_t)h * W + w;
+                xout[l] = __ldcs(g4 + l) + __ldcs(g4 + 2 * dstep + (L - 1 - l)) + tile[j][tx];
+            }
+        }
+    }
+}
+
+// ---- y (B, L, 4, d) fp32 (the SSD output, direction-major heads) -> out (B, L, d):
+//      out[b, hW+w] = y[b, hW+w, 0] + y[b, L-1-(hW+w), 2] + y[b, wH+h, 1] + y[b, L-1-(wH+h), 3]   (SSD/MedSSD.py:380-391)
+//      and its adjoint (every y row receives exactly one out row): rows of d contiguous floats, gathers only
+template <bool BWD>
+__global__ void __launch_bounds__(256) ssd_merge4_kernel(const float* __restrict__ src, float* __restrict__ dst, int d, int H, int W, int64_t total) {
+    const int L = H * W;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (!BWD) {   // idx over (b, l, j)
+            const int j = (int)(idx % d);
+            const int64_t bl = idx / d;
+            const int l = (int)(bl % L);
+            const int64_t b = bl / L;
+            const int h = l / W, w = l % W, lt = w * H + h;
+            const float* yb = src + (size_t)b * L * 4 * d + j;
+            dst[idx] = __ldcs(yb + ((size_t)l * 4 + 0) * d) + __ldcs(yb + ((size_t)(L - 1 - l) * 4 + 2) * d) +
+                       __ldcs(yb + ((size_t)lt * 4 + 1) * d) + __ldcs(yb + ((size_t)(L - 1 - lt) * 4 + 3) * d);
+        } else {      // idx over (b, l', k, j): dy[b, l', k] = dout[b, l(l', k)]
+            const int j = (int)(idx % d);
+            int64_t r = idx / d;
+            const int k = (int)(r & 3);
+            r >>= 2;
+            const int lp = (int)(r % L);
+            const int64_t b = r / L;
+            int l = (k & 2) ? L - 1 - lp : lp;            // undo the reversal
+            if (k & 1) l = (l % H) * W + l / H;           // column-major index w H + h -> row-major h W + w
+            dst[idx] = __ldcs(src + ((size_t)b * L + l) * d + j);
+        }
+    }
+}
+
 static int check_dims(const void* a, const void* b, int batch, int D, int H, int W, int dtype, const char* who) {
     B200_REQUIRE(a && b, "%s: NULL tensor", who);
     B200_REQUIRE(batch > 0 && D > 0 && H > 0 && W > 0, "%s: non-positive size", who);
@@ -214,4 +308,35 @@ extern "C" int b200_cross_merge_bwd(const void* dy, void* dys, int32_t batch, in
                                     b200_stream_t stream) {
     if (int rc = check_dims(dy, dys, batch, D, H, W, dtype, "b200_cross_merge_bwd")) return rc;
     DISPATCH(run_merge, dy, dys, batch, D, H, W, true, (cudaStream_t)stream)
+}
+
+extern "C" int b200_cross_scan4(const float* x, int64_t x_batch_stride, float* x4, int32_t batch, int32_t C, int32_t H, int32_t W,
+                                b200_stream_t stream) {
+    if (int rc = check_dims(x, x4, batch, C, H, W, B200_F32, "b200_cross_scan4")) return rc;
+    dim3 grid(batch * C, (W + 31) / 32, (H + 31) / 32);
+    cross_scan4_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_batch_stride, x4, C, H, W);
+    return check_launch("cross_scan4_kernel");
+}
+extern "C" int b200_cross_scan4_bwd(const float* dx4, float* dx, int64_t dx_batch_stride, int32_t batch, int32_t C, int32_t H, int32_t W,
+                                    b200_stream_t stream) {
+    if (int rc = check_dims(dx4, dx, batch, C, H, W, B200_F32, "b200_cross_scan4_bwd")) return rc;
+    dim3 grid(batch * C, (W + 31) / 32, (H + 31) / 32);
+    cross_scan4_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dx4, dx_batch_stride, dx, C, H, W);
+    return check_launch("cross_scan4_bwd_kernel");
+}
+static unsigned merge4_grid(int64_t total) {
+    const int64_t want = (total + 255) / 256;
+    return (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+}
+extern "C" int b200_ssd_merge4(const float* y, float* out, int32_t batch, int32_t d, int32_t H, int32_t W, b200_stream_t stream) {
+    if (int rc = check_dims(y, out, batch, d, H, W, B200_F32, "b200_ssd_merge4")) return rc;
+    const int64_t total = (int64_t)batch * H * W * d;
+    ssd_merge4_kernel<false><<<merge4_grid(total), 256, 0, (cudaStream_t)stream>>>(y, out, d, H, W, total);
+    return check_launch("ssd_merge4_kernel");
+}
+extern "C" int b200_ssd_merge4_bwd(const float* dout, float* dy, int32_t batch, int32_t d, int32_t H, int32_t W, b200_stream_t stream) {
+    if (int rc = check_dims(dout, dy, batch, d, H, W, B200_F32, "b200_ssd_merge4_bwd")) return rc;
+    const int64_t total = (int64_t)batch * H * W * 4 * d;
+    ssd_merge4_kernel<true><<<merge4_grid(total), 256, 0, (cudaStream_t)stream>>>(dout, dy, d, H, W, total);
+    return check_launch("ssd_merge4_bwd_kernel");
 }

@@ -82,11 +82,15 @@ class SS2D_with_SSD(nn.Module):
         else:
             xBCdt = self.act(self.conv2d(xBCdt.permute(0, 3, 1, 2).contiguous()))       # (B, c, H, W)
 
-        # cross-scan of x, B, C and dt together (SSD/MedSSD.py:332-336)
-        hwwh = torch.stack([xBCdt.reshape(B, -1, L), xBCdt.transpose(2, 3).reshape(B, -1, L)], dim=1)
-        xBCdts = torch.cat([hwwh, hwwh.flip(-1)], dim=1)                                  # (B, 4, c, L)
+        # cross-scan of x, B, C and dt (SSD/MedSSD.py:332-336)
         gn = self.ngroups * self.d_state
-        xs, Bs, Cs, dts = torch.split(xBCdts, [self.d_ssm, gn, gn, self.nheads], dim=2)
+        if xBCdt.is_cuda:   # one pass per component (csrc/cross.cu::cross_scan4_kernel), channel slices read in place
+            from .cross import cross_scan4
+            xs, Bs, Cs, dts = (cross_scan4(t) for t in torch.split(xBCdt, [self.d_ssm, gn, gn, self.nheads], dim=1))
+        else:
+            hwwh = torch.stack([xBCdt.reshape(B, -1, L), xBCdt.transpose(2, 3).reshape(B, -1, L)], dim=1)
+            xBCdts = torch.cat([hwwh, hwwh.flip(-1)], dim=1)                              # (B, 4, c, L)
+            xs, Bs, Cs, dts = torch.split(xBCdts, [self.d_ssm, gn, gn, self.nheads], dim=2)
         # (b, l, k*d) views with L stride 1 -- never made contiguous (SSD/MedSSD.py:344-347)
         xs = xs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (-1, self.headdim))     # (B, L, 4*nheads, P)
         Bs = Bs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (self.ngroups, -1))     # (B, L, G, 4*N)
@@ -102,10 +106,14 @@ class SS2D_with_SSD(nn.Module):
         assert y.dtype == torch.float32
 
         # cross-merge in the (B, L, K, d) layout (SSD/MedSSD.py:380-391)
-        inv_y = y[:, :, 2:4].flip(1)
-        wh_y = y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
-        invwh_y = inv_y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
-        out = (y[:, :, 0] + inv_y[:, :, 0] + wh_y + invwh_y).view(B, H, W, -1)
+        if y.is_cuda:
+            from .cross import ssd_merge4
+            out = ssd_merge4(y, H, W).view(B, H, W, -1)                                         # one gather pass (csrc/cross.cu)
+        else:
+            inv_y = y[:, :, 2:4].flip(1)
+            wh_y = y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
+            invwh_y = inv_y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
+            out = (y[:, :, 0] + inv_y[:, :, 0] + wh_y + invwh_y).view(B, H, W, -1)
 
         if self.rmsnorm:
             out = self.norm(out, z)

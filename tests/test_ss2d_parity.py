@@ -126,3 +126,38 @@ def test_vssm_tiny_matches_reference():
                 assert relerr(p.grad, ref) < 2e-3, k
                 checked += 1
     assert checked > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 5, 7, 6), (1, 3, 56, 56), (2, 40, 14, 14), (1, 2, 33, 35)])
+def test_ssd_twin_cross_scan4_and_merge4_are_bit_exact(shape):
+    """SSD twin of the cross-scan / cross-merge (csrc/cross.cu) against the reference's tensor ops
+    (SSD/MedSSD.py:332-336, 376-391): pure data movement + 3 adds in the reference's association order."""
+    from medical_image_classification_b200.cross import cross_scan4, ssd_merge4
+    B, C, H, W = shape
+    L = H * W
+    torch.manual_seed(C)
+    wide = torch.randn(B, C + 3, H, W, device="cuda").requires_grad_()
+    x = wide[:, 1:1 + C]                                     # a channel slice, read in place
+    x4 = cross_scan4(x)
+    hwwh = torch.stack([x.reshape(B, -1, L), x.transpose(2, 3).reshape(B, -1, L)], dim=1)
+    ref4 = torch.cat([hwwh, hwwh.flip(-1)], dim=1)
+    assert torch.equal(x4, ref4)
+    g4 = torch.randn_like(x4)
+    x4.backward(g4)
+    got = wide.grad.clone(); wide.grad = None
+    ref4.backward(g4)
+    assert torch.allclose(got, wide.grad, rtol=0, atol=1e-6)   # 4-term sum, association may differ
+    d = 8
+    y = torch.randn(B, L, 4, d, device="cuda").requires_grad_()
+    out = ssd_merge4(y, H, W)
+    inv_y = y[:, :, 2:4].flip(1)
+    wh_y = y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
+    invwh_y = inv_y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
+    ref = y[:, :, 0] + inv_y[:, :, 0] + wh_y + invwh_y
+    assert torch.allclose(out, ref, rtol=0, atol=2e-6)
+    go = torch.randn_like(out)
+    out.backward(go)
+    got = y.grad.clone(); y.grad = None
+    ref.backward(go)
+    assert torch.equal(got, y.grad)
