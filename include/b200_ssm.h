@@ -234,21 +234,22 @@ int b200_rmsnorm_gated_bwd(const float* x, const float* z, const float* w, const
  * `y = self.out_norm(y); y = y * F.silu(z)` (reference MedMamba.py:478-479; nn.LayerNorm(d_inner), eps 1e-5)
  * and the four autograd kernels behind it.
  *   z == NULL (and dz == NULL) gives the plain LayerNorm of the block's pre-norm (MedMamba.py:531 `self.ln_1`).
- *   y (rows, D) f32 with row stride y_row_stride (the cross-merge output, or the right half of the block input read
- *   in place); z (rows, D) with row stride z_row_stride (the second
+ *   y (rows, D) y_dtype in {F32, BF16} with row stride y_row_stride (the cross-merge output, or the right half of the
+ *   block input read in place; BF16 -- the residual stream of an autocast model after PatchMerging's Linear -- only with
+ *   z == NULL); z (rows, D) with row stride z_row_stride (the second
  *   half of in_proj's output, read in place), z_dtype in {F32, BF16}; w, b (D) f32; out (rows, D) out_dtype
  *   in {F32, BF16 (= what the following Linear would cast to under autocast)}; mean, rstd (rows) f32 kept for
- *   the backward.  Backward: dout (rows, D) out_dtype -> dy (rows, D) f32, dz (rows, D) z_dtype contiguous,
+ *   the backward.  Backward: dout (rows, D) out_dtype -> dy (rows, D) y_dtype, dz (rows, D) z_dtype contiguous,
  *   dw_partial / db_partial (b200_ln_gate_grid(rows), D) f32 per-CTA partial sums (the caller adds the rows up).
  *   D <= 1024.
  * ------------------------------------------------------------------------------------------ */
 int b200_ln_gate_grid(int64_t rows);
-int b200_ln_gate_fwd(const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
-                     const float* b, void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
-                     b200_stream_t stream);
-int b200_ln_gate_bwd(const void* dout, const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype,
-                     const float* w, const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
-                     float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream);
+int b200_ln_gate_fwd(const void* y, int32_t y_dtype, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype,
+                     const float* w, const float* b, void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D,
+                     float eps, b200_stream_t stream);
+int b200_ln_gate_bwd(const void* dout, const void* y, int32_t y_dtype, int64_t y_row_stride, const void* z, int64_t z_row_stride,
+                     int32_t z_dtype, const float* w, const float* b, int32_t out_dtype, const float* mean, const float* rstd, void* dy,
+                     void* dz, float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * SS2D producer stage: x = SiLU(depthwise conv3x3(x_in) + bias) -- replaces
@@ -271,14 +272,15 @@ int b200_dwconv_silu_bwd(const float* gout, const void* xin, int64_t pix_stride,
  * permute / cat / shuffle copy / residual add of SS_Conv_SSM.forward (reference MedMamba.py:486-499, 533-538).
  *   left (B, c, P) planes, or (B, P, c) when left_channels_last (the conv branch run in torch.channels_last; P = H*W),
  *   and x (B, P, c) channels-last (the SS2D branch), both lx_dtype
- *   in {F32, BF16}; input, out (B, P, 2 c) f32.  out[b,p,2j] = left[b,j,p] + input[b,p,2j];
- *   out[b,p,2j+1] = x[b,p,j] + input[b,p,2j+1].  Backward: dout (B, P, 2 c) f32 -> dleft (B, c, P), dx (B, P, c)
- *   in lx_dtype (the gradient of `input` is dout itself).
+ *   in {F32, BF16}; input, out (B, P, 2 c) io_dtype: F32, or BF16 with BF16 left / x (the residual stream of an autocast
+ *   model is bf16 after PatchMerging's Linear; the sum is formed in fp32 and rounded once, as torch does).
+ *   out[b,p,2j] = left[b,j,p] + input[b,p,2j]; out[b,p,2j+1] = x[b,p,j] + input[b,p,2j+1].
+ *   Backward: dout (B, P, 2 c) io_dtype -> dleft (B, c, P), dx (B, P, c) in lx_dtype (the gradient of `input` is dout).
  * ------------------------------------------------------------------------------------------ */
-int b200_shuffle_cat_add_fwd(const void* left, int32_t left_channels_last, const void* x, int32_t lx_dtype, const float* input,
-                             float* out, int32_t B, int32_t c, int32_t P, b200_stream_t stream);
-int b200_shuffle_cat_add_bwd(const float* dout, void* dleft, int32_t left_channels_last, void* dx, int32_t lx_dtype, int32_t B,
-                             int32_t c, int32_t P, b200_stream_t stream);
+int b200_shuffle_cat_add_fwd(const void* left, int32_t left_channels_last, const void* x, int32_t lx_dtype, const void* input,
+                             void* out, int32_t io_dtype, int32_t B, int32_t c, int32_t P, b200_stream_t stream);
+int b200_shuffle_cat_add_bwd(const void* dout, int32_t io_dtype, void* dleft, int32_t left_channels_last, void* dx, int32_t lx_dtype,
+                             int32_t B, int32_t c, int32_t P, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------ */
 const char* b200_last_error(void);   /* thread-local message of the last failing call */

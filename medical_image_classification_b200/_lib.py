@@ -126,11 +126,11 @@ def load() -> C.CDLL:
     lib.b200_rmsnorm_gated_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, vp]
     lib.b200_dwconv_silu_fwd.argtypes = [vp, i64, i32, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_dwconv_silu_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
-    lib.b200_shuffle_cat_add_fwd.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, vp]
-    lib.b200_shuffle_cat_add_bwd.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, vp]
+    lib.b200_shuffle_cat_add_fwd.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp]
+    lib.b200_shuffle_cat_add_bwd.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]
     lib.b200_ln_gate_grid.argtypes = [i64]
-    lib.b200_ln_gate_fwd.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]
-    lib.b200_ln_gate_bwd.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp]
+    lib.b200_ln_gate_fwd.argtypes = [vp, i32, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]
+    lib.b200_ln_gate_bwd.argtypes = [vp, vp, i32, i64, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp]
     for which, st in enumerate((SScanFwdParams, SScanBwdParams, SsdFwdParams, SsdBwdParams)):
         if lib.b200_sizeof_params(which) != C.sizeof(st):
             raise RuntimeError(f"libb200ssm ABI mismatch for {st.__name__}: "

@@ -10,9 +10,25 @@
 
 namespace b200 {
 
-template <typename TL>
+// element pair idx of a channels-last row buffer (fp32: one float2, bf16: one 32-bit word), streaming
+template <typename T> __device__ __forceinline__ float2 ld_pair(const T* base, int64_t idx);
+template <> __device__ __forceinline__ float2 ld_pair<float>(const float* base, int64_t idx) { return __ldcs(reinterpret_cast<const float2*>(base) + idx); }
+template <> __device__ __forceinline__ float2 ld_pair<__nv_bfloat16>(const __nv_bfloat16* base, int64_t idx) {
+    const unsigned w = __ldcs(reinterpret_cast<const unsigned*>(base) + idx);
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <typename T> __device__ __forceinline__ void st_pair(T* base, int64_t idx, float a, float b);
+template <> __device__ __forceinline__ void st_pair<float>(float* base, int64_t idx, float a, float b) {
+    __stcs(reinterpret_cast<float2*>(base) + idx, make_float2(a, b));
+}
+template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16* base, int64_t idx, float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    __stcs(reinterpret_cast<unsigned*>(base) + idx, *reinterpret_cast<const unsigned*>(&v));
+}
+
+template <typename TL, typename TIO>
 __global__ void __launch_bounds__(256) shuffle_cat_add_fwd_kernel(const TL* __restrict__ left, const TL* __restrict__ x,
-                                                                  const float* __restrict__ input, float* __restrict__ out, int c, int P) {
+                                                                  const TIO* __restrict__ input, TIO* __restrict__ out, int c, int P) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, j0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -27,15 +43,15 @@ __global__ void __launch_bounds__(256) shuffle_cat_add_fwd_kernel(const TL* __re
         const int p = p0 + r, j = j0 + tx;
         if (p < P && j < c) {
             const size_t row = (size_t)b * P + p;
-            const float2 in2 = __ldcs(reinterpret_cast<const float2*>(input + row * 2 * c) + j);
+            const float2 in2 = ld_pair<TIO>(input, (int64_t)row * c + j);
             const float xv = ldg_stream(x + row * c + j);
-            __stcs(reinterpret_cast<float2*>(out + row * 2 * c) + j, make_float2(tile[tx][r] + in2.x, xv + in2.y));
+            st_pair<TIO>(out, (int64_t)row * c + j, tile[tx][r] + in2.x, xv + in2.y);
         }
     }
 }
 
-template <typename TL>
-__global__ void __launch_bounds__(256) shuffle_cat_add_bwd_kernel(const float* __restrict__ dout, TL* __restrict__ dleft, TL* __restrict__ dx, int c,
+template <typename TL, typename TIO>
+__global__ void __launch_bounds__(256) shuffle_cat_add_bwd_kernel(const TIO* __restrict__ dout, TL* __restrict__ dleft, TL* __restrict__ dx, int c,
                                                                   int P) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, j0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -46,7 +62,7 @@ __global__ void __launch_bounds__(256) shuffle_cat_add_bwd_kernel(const float* _
         float2 g = make_float2(0.f, 0.f);
         if (p < P && j < c) {
             const size_t row = (size_t)b * P + p;
-            g = __ldcs(reinterpret_cast<const float2*>(dout + row * 2 * c) + j);
+            g = ld_pair<TIO>(dout, (int64_t)row * c + j);
             stg_stream(dx + row * c + j, g.y);
         }
         tile[r][tx] = g.x;
@@ -60,66 +76,79 @@ __global__ void __launch_bounds__(256) shuffle_cat_add_bwd_kernel(const float* _
 }
 
 // left already channels-last (B, P, c): a pure interleave, two rows of c -> one row of 2 c
-template <typename TL>
+template <typename TL, typename TIO>
 __global__ void __launch_bounds__(256) shuffle_cat_add_cl_fwd_kernel(const TL* __restrict__ left, const TL* __restrict__ x,
-                                                                     const float* __restrict__ input, float* __restrict__ out, int c, int64_t rows) {
+                                                                     const TIO* __restrict__ input, TIO* __restrict__ out, int c, int64_t rows) {
     const int64_t total = rows * c;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const float2 in2 = __ldcs(reinterpret_cast<const float2*>(input) + idx);   // (row, 2 j), (row, 2 j + 1)
-        __stcs(reinterpret_cast<float2*>(out) + idx, make_float2(ldg_stream(left + idx) + in2.x, ldg_stream(x + idx) + in2.y));
+        const float2 in2 = ld_pair<TIO>(input, idx);   // (row, 2 j), (row, 2 j + 1)
+        st_pair<TIO>(out, idx, ldg_stream(left + idx) + in2.x, ldg_stream(x + idx) + in2.y);
     }
 }
-template <typename TL>
-__global__ void __launch_bounds__(256) shuffle_cat_add_cl_bwd_kernel(const float* __restrict__ dout, TL* __restrict__ dleft, TL* __restrict__ dx,
+template <typename TL, typename TIO>
+__global__ void __launch_bounds__(256) shuffle_cat_add_cl_bwd_kernel(const TIO* __restrict__ dout, TL* __restrict__ dleft, TL* __restrict__ dx,
                                                                      int c, int64_t rows) {
     const int64_t total = rows * c;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const float2 g = __ldcs(reinterpret_cast<const float2*>(dout) + idx);
+        const float2 g = ld_pair<TIO>(dout, idx);
         stg_stream(dleft + idx, g.x);
         stg_stream(dx + idx, g.y);
     }
+}
+
+static unsigned cl_grid(int64_t rows, int c) {
+    const int64_t want = (rows * c + 255) / 256;
+    return (unsigned)(want < 148 * 16 ? want : 148 * 16);
+}
+template <typename TL, typename TIO>
+static int glue_fwd(const void* left, int cl, const void* x, const void* input, void* out, int B, int c, int P, cudaStream_t st) {
+    if (cl) {
+        const int64_t rows = (int64_t)B * P;
+        shuffle_cat_add_cl_fwd_kernel<TL, TIO><<<cl_grid(rows, c), 256, 0, st>>>((const TL*)left, (const TL*)x, (const TIO*)input, (TIO*)out, c, rows);
+        return check_launch("shuffle_cat_add_cl_fwd_kernel");
+    }
+    const dim3 grid((P + 31) / 32, (c + 31) / 32, B);
+    shuffle_cat_add_fwd_kernel<TL, TIO><<<grid, 256, 0, st>>>((const TL*)left, (const TL*)x, (const TIO*)input, (TIO*)out, c, P);
+    return check_launch("shuffle_cat_add_fwd_kernel");
+}
+template <typename TL, typename TIO>
+static int glue_bwd(const void* dout, void* dleft, int cl, void* dx, int B, int c, int P, cudaStream_t st) {
+    if (cl) {
+        const int64_t rows = (int64_t)B * P;
+        shuffle_cat_add_cl_bwd_kernel<TL, TIO><<<cl_grid(rows, c), 256, 0, st>>>((const TIO*)dout, (TL*)dleft, (TL*)dx, c, rows);
+        return check_launch("shuffle_cat_add_cl_bwd_kernel");
+    }
+    const dim3 grid((P + 31) / 32, (c + 31) / 32, B);
+    shuffle_cat_add_bwd_kernel<TL, TIO><<<grid, 256, 0, st>>>((const TIO*)dout, (TL*)dleft, (TL*)dx, c, P);
+    return check_launch("shuffle_cat_add_bwd_kernel");
 }
 
 }  // namespace b200
 
 using namespace b200;
 
-extern "C" int b200_shuffle_cat_add_fwd(const void* left, int32_t left_channels_last, const void* x, int32_t lx_dtype, const float* input,
-                                        float* out, int32_t B, int32_t c, int32_t P, b200_stream_t stream) {
+// (left / x dtype, input / out dtype): f32 x f32; bf16 x f32 (stage 0 of an autocast model: fp32 residual stream); bf16 x bf16
+// (after PatchMerging's Linear the residual stream of an autocast model is bf16)
+extern "C" int b200_shuffle_cat_add_fwd(const void* left, int32_t left_channels_last, const void* x, int32_t lx_dtype, const void* input,
+                                        void* out, int32_t io_dtype, int32_t B, int32_t c, int32_t P, b200_stream_t stream) {
     B200_REQUIRE(left && x && input && out, "b200_shuffle_cat_add_fwd: NULL argument");
     B200_REQUIRE(B > 0 && c > 0 && P > 0 && B <= 65535, "b200_shuffle_cat_add_fwd: bad shape");
-    B200_REQUIRE(lx_dtype == B200_F32 || lx_dtype == B200_BF16, "b200_shuffle_cat_add_fwd: left / x dtype must be f32 or bf16");
-    const dim3 grid((P + 31) / 32, (c + 31) / 32, B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (left_channels_last) {
-        const int64_t rows = (int64_t)B * P;
-        const int64_t want = (rows * c + 255) / 256;
-        const unsigned g1 = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-        if (lx_dtype == B200_F32) shuffle_cat_add_cl_fwd_kernel<float><<<g1, 256, 0, st>>>((const float*)left, (const float*)x, input, out, c, rows);
-        else shuffle_cat_add_cl_fwd_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>((const __nv_bfloat16*)left, (const __nv_bfloat16*)x, input, out, c, rows);
-        return check_launch("shuffle_cat_add_cl_fwd_kernel");
-    }
-    if (lx_dtype == B200_F32) shuffle_cat_add_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)left, (const float*)x, input, out, c, P);
-    else shuffle_cat_add_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)left, (const __nv_bfloat16*)x, input, out, c, P);
-    return check_launch("shuffle_cat_add_fwd_kernel");
+    if (lx_dtype == B200_F32 && io_dtype == B200_F32) return glue_fwd<float, float>(left, left_channels_last, x, input, out, B, c, P, st);
+    if (lx_dtype == B200_BF16 && io_dtype == B200_F32) return glue_fwd<__nv_bfloat16, float>(left, left_channels_last, x, input, out, B, c, P, st);
+    if (lx_dtype == B200_BF16 && io_dtype == B200_BF16)
+        return glue_fwd<__nv_bfloat16, __nv_bfloat16>(left, left_channels_last, x, input, out, B, c, P, st);
+    B200_REQUIRE(false, "b200_shuffle_cat_add_fwd: unsupported dtypes left/x = %d, input/out = %d", lx_dtype, io_dtype);
 }
 
-extern "C" int b200_shuffle_cat_add_bwd(const float* dout, void* dleft, int32_t left_channels_last, void* dx, int32_t lx_dtype, int32_t B,
-                                        int32_t c, int32_t P, b200_stream_t stream) {
+extern "C" int b200_shuffle_cat_add_bwd(const void* dout, int32_t io_dtype, void* dleft, int32_t left_channels_last, void* dx, int32_t lx_dtype,
+                                        int32_t B, int32_t c, int32_t P, b200_stream_t stream) {
     B200_REQUIRE(dout && dleft && dx, "b200_shuffle_cat_add_bwd: NULL argument");
     B200_REQUIRE(B > 0 && c > 0 && P > 0 && B <= 65535, "b200_shuffle_cat_add_bwd: bad shape");
-    B200_REQUIRE(lx_dtype == B200_F32 || lx_dtype == B200_BF16, "b200_shuffle_cat_add_bwd: left / x dtype must be f32 or bf16");
-    const dim3 grid((P + 31) / 32, (c + 31) / 32, B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (left_channels_last) {
-        const int64_t rows = (int64_t)B * P;
-        const int64_t want = (rows * c + 255) / 256;
-        const unsigned g1 = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-        if (lx_dtype == B200_F32) shuffle_cat_add_cl_bwd_kernel<float><<<g1, 256, 0, st>>>(dout, (float*)dleft, (float*)dx, c, rows);
-        else shuffle_cat_add_cl_bwd_kernel<__nv_bfloat16><<<g1, 256, 0, st>>>(dout, (__nv_bfloat16*)dleft, (__nv_bfloat16*)dx, c, rows);
-        return check_launch("shuffle_cat_add_cl_bwd_kernel");
-    }
-    if (lx_dtype == B200_F32) shuffle_cat_add_bwd_kernel<float><<<grid, 256, 0, st>>>(dout, (float*)dleft, (float*)dx, c, P);
-    else shuffle_cat_add_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(dout, (__nv_bfloat16*)dleft, (__nv_bfloat16*)dx, c, P);
-    return check_launch("shuffle_cat_add_bwd_kernel");
+    if (lx_dtype == B200_F32 && io_dtype == B200_F32) return glue_bwd<float, float>(dout, dleft, left_channels_last, dx, B, c, P, st);
+    if (lx_dtype == B200_BF16 && io_dtype == B200_F32) return glue_bwd<__nv_bfloat16, float>(dout, dleft, left_channels_last, dx, B, c, P, st);
+    if (lx_dtype == B200_BF16 && io_dtype == B200_BF16)
+        return glue_bwd<__nv_bfloat16, __nv_bfloat16>(dout, dleft, left_channels_last, dx, B, c, P, st);
+    B200_REQUIRE(false, "b200_shuffle_cat_add_bwd: unsupported dtypes left/x = %d, dout = %d", lx_dtype, io_dtype);
 }

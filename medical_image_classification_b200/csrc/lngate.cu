@@ -11,6 +11,8 @@
 //   dn = dout * silu(z)           dz = dout * n * sigmoid(z) * (1 + z * (1 - sigmoid(z)))
 //   dw = sum_rows dn * xhat       db = sum_rows dn
 //   dy = rstd * (dn*w - mean_D(dn*w) - xhat * mean_D(dn*w * xhat))
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -24,8 +26,8 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <typename TZ, typename TO, int NPL, bool HAS_Z>
-__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float* __restrict__ y, int64_t y_row_stride, const TZ* __restrict__ z,
+template <typename TY, typename TZ, typename TO, int NPL, bool HAS_Z>
+__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const TY* __restrict__ y, int64_t y_row_stride, const TZ* __restrict__ z,
                                                                     int64_t z_row_stride,
                                                                     const float* __restrict__ w, const float* __restrict__ b,
                                                                     TO* __restrict__ out, float* __restrict__ mean, float* __restrict__ rstd,
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float*
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int c = lane + 32 * k;
-            v[k] = c < D ? __ldcs(y + r * y_row_stride + c) : 0.f;
+            v[k] = c < D ? ldg_stream(y + r * y_row_stride + c) : 0.f;
             s += v[k];
         }
         const float mu = warp_sum(s) * invD;
@@ -71,11 +73,11 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const float*
     }
 }
 
-template <typename TZ, typename TO, int NPL, bool HAS_Z>
-__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __restrict__ dout, const float* __restrict__ y, int64_t y_row_stride,
+template <typename TY, typename TZ, typename TO, int NPL, bool HAS_Z>
+__global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __restrict__ dout, const TY* __restrict__ y, int64_t y_row_stride,
                                                                     const TZ* __restrict__ z, int64_t z_row_stride, const float* __restrict__ w,
                                                                     const float* __restrict__ b, const float* __restrict__ mean,
-                                                                    const float* __restrict__ rstd, float* __restrict__ dy, TZ* __restrict__ dz,
+                                                                    const float* __restrict__ rstd, TY* __restrict__ dy, TZ* __restrict__ dz,
                                                                     float* __restrict__ dw_part, float* __restrict__ db_part, int64_t rows, int D) {
     __shared__ float red[LG_WARPS][32 * NPL];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __
             xh[k] = 0.f;
             g[k] = 0.f;
             if (c < D) {
-                const float yy = __ldcs(y + r * y_row_stride + c);
+                const float yy = ldg_stream(y + r * y_row_stride + c);
                 const float go = ldg_stream(dout + r * D + c);
                 const float wc = __ldg(w + c);
                 xh[k] = (yy - mu) * rs;
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int c = lane + 32 * k;
-            if (c < D) __stcs(dy + r * D + c, rs * (g[k] - m1 - xh[k] * m2));
+            if (c < D) stg_stream(dy + r * D + c, rs * (g[k] - m1 - xh[k] * m2));
         }
     }
     // d(weight), d(bias): combine the CTA's warps, write one partial row per CTA
@@ -144,55 +146,58 @@ static int lg_grid(int64_t rows) {
     return (int)(want < 148 * 4 ? (want < 1 ? 1 : want) : 148 * 4);
 }
 
-template <typename TZ, typename TO, int NPL>
+template <typename TY, typename TZ, typename TO, int NPL>
 static int lg_fwd_launch(const void* y, int64_t ys, const void* z, int64_t zs, const float* w, const float* b, void* out, float* mean, float* rstd,
                          int64_t rows, int D, float eps, cudaStream_t st) {
-    if (z)
-        ln_gate_fwd_kernel<TZ, TO, NPL, true><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const float*)y, ys, (const TZ*)z, zs, w, b, (TO*)out, mean,
-                                                                                       rstd, rows, D, eps);
-    else
-        ln_gate_fwd_kernel<TZ, TO, NPL, false><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const float*)y, ys, (const TZ*)z, zs, w, b, (TO*)out, mean,
+    if constexpr (std::is_same<TY, float>::value) {
+        if (z) {
+            ln_gate_fwd_kernel<TY, TZ, TO, NPL, true><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TY*)y, ys, (const TZ*)z, zs, w, b, (TO*)out,
+                                                                                               mean, rstd, rows, D, eps);
+            return check_launch("ln_gate_fwd_kernel");
+        }
+    }
+    ln_gate_fwd_kernel<TY, TZ, TO, NPL, false><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TY*)y, ys, (const TZ*)z, zs, w, b, (TO*)out, mean,
                                                                                         rstd, rows, D, eps);
     return check_launch("ln_gate_fwd_kernel");
 }
-template <typename TZ, typename TO, int NPL>
+template <typename TY, typename TZ, typename TO, int NPL>
 static int lg_bwd_launch(const void* dout, const void* y, int64_t ys, const void* z, int64_t zs, const float* w, const float* b, const float* mean,
-                         const float* rstd, float* dy, void* dz, float* dwp, float* dbp, int64_t rows, int D, cudaStream_t st) {
-    if (z)
-        ln_gate_bwd_kernel<TZ, TO, NPL, true><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const float*)y, ys, (const TZ*)z, zs, w, b,
-                                                                                       mean, rstd, dy, (TZ*)dz, dwp, dbp, rows, D);
-    else
-        ln_gate_bwd_kernel<TZ, TO, NPL, false><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const float*)y, ys, (const TZ*)z, zs, w, b,
-                                                                                        mean, rstd, dy, (TZ*)dz, dwp, dbp, rows, D);
+                         const float* rstd, void* dy, void* dz, float* dwp, float* dbp, int64_t rows, int D, cudaStream_t st) {
+    if constexpr (std::is_same<TY, float>::value) {
+        if (z) {
+            ln_gate_bwd_kernel<TY, TZ, TO, NPL, true><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const TY*)y, ys, (const TZ*)z, zs, w,
+                                                                                               b, mean, rstd, (TY*)dy, (TZ*)dz, dwp, dbp, rows, D);
+            return check_launch("ln_gate_bwd_kernel");
+        }
+    }
+    ln_gate_bwd_kernel<TY, TZ, TO, NPL, false><<<lg_grid(rows), LG_WARPS * 32, 0, st>>>((const TO*)dout, (const TY*)y, ys, (const TZ*)z, zs, w, b,
+                                                                                        mean, rstd, (TY*)dy, (TZ*)dz, dwp, dbp, rows, D);
     return check_launch("ln_gate_bwd_kernel");
 }
 
-// dispatch on (z dtype, out dtype, columns per lane)
-#define LG_DISPATCH(FN, ...)                                                                  \
-    do {                                                                                      \
-        const int npl = (D + 31) / 32;                                                        \
-        if (z_dtype == B200_F32 && out_dtype == B200_F32) {                                   \
-            if (npl <= 4) return FN<float, float, 4>(__VA_ARGS__);                            \
-            if (npl <= 8) return FN<float, float, 8>(__VA_ARGS__);                            \
-            if (npl <= 16) return FN<float, float, 16>(__VA_ARGS__);                          \
-            if (npl <= 24) return FN<float, float, 24>(__VA_ARGS__);                          \
-            return FN<float, float, 32>(__VA_ARGS__);                                         \
-        }                                                                                     \
-        if (z_dtype == B200_BF16 && out_dtype == B200_BF16) {                                 \
-            if (npl <= 4) return FN<__nv_bfloat16, __nv_bfloat16, 4>(__VA_ARGS__);            \
-            if (npl <= 8) return FN<__nv_bfloat16, __nv_bfloat16, 8>(__VA_ARGS__);            \
-            if (npl <= 16) return FN<__nv_bfloat16, __nv_bfloat16, 16>(__VA_ARGS__);          \
-            if (npl <= 24) return FN<__nv_bfloat16, __nv_bfloat16, 24>(__VA_ARGS__);          \
-            return FN<__nv_bfloat16, __nv_bfloat16, 32>(__VA_ARGS__);                         \
-        }                                                                                     \
-        if (z_dtype == B200_BF16 && out_dtype == B200_F32) {                                  \
-            if (npl <= 4) return FN<__nv_bfloat16, float, 4>(__VA_ARGS__);                    \
-            if (npl <= 8) return FN<__nv_bfloat16, float, 8>(__VA_ARGS__);                    \
-            if (npl <= 16) return FN<__nv_bfloat16, float, 16>(__VA_ARGS__);                  \
-            if (npl <= 24) return FN<__nv_bfloat16, float, 24>(__VA_ARGS__);                  \
-            return FN<__nv_bfloat16, float, 32>(__VA_ARGS__);                                 \
-        }                                                                                     \
-        B200_REQUIRE(false, "b200_ln_gate: unsupported dtype combination z=%d out=%d", z_dtype, out_dtype); \
+// dispatch on (y dtype, z dtype, out dtype, columns per lane); a bf16 y (the bf16 residual stream of an autocast model) is the
+// plain-LayerNorm case only (z == NULL)
+#define LG_NPL(FN, TY, TZ, TO, ...)                                    \
+    do {                                                               \
+        const int npl = (D + 31) / 32;                                 \
+        if (npl <= 4) return FN<TY, TZ, TO, 4>(__VA_ARGS__);           \
+        if (npl <= 8) return FN<TY, TZ, TO, 8>(__VA_ARGS__);           \
+        if (npl <= 16) return FN<TY, TZ, TO, 16>(__VA_ARGS__);         \
+        if (npl <= 24) return FN<TY, TZ, TO, 24>(__VA_ARGS__);         \
+        return FN<TY, TZ, TO, 32>(__VA_ARGS__);                        \
+    } while (0)
+#define LG_DISPATCH(FN, ...)                                                                                       \
+    do {                                                                                                           \
+        if (y_dtype == B200_BF16) {                                                                                \
+            B200_REQUIRE(z == nullptr, "b200_ln_gate: a bf16 y is supported without z only");                      \
+            if (out_dtype == B200_BF16) LG_NPL(FN, __nv_bfloat16, __nv_bfloat16, __nv_bfloat16, __VA_ARGS__);      \
+            if (out_dtype == B200_F32) LG_NPL(FN, __nv_bfloat16, float, float, __VA_ARGS__);                       \
+        } else if (y_dtype == B200_F32) {                                                                          \
+            if (z_dtype == B200_F32 && out_dtype == B200_F32) LG_NPL(FN, float, float, float, __VA_ARGS__);        \
+            if (z_dtype == B200_BF16 && out_dtype == B200_BF16) LG_NPL(FN, float, __nv_bfloat16, __nv_bfloat16, __VA_ARGS__); \
+            if (z_dtype == B200_BF16 && out_dtype == B200_F32) LG_NPL(FN, float, __nv_bfloat16, float, __VA_ARGS__); \
+        }                                                                                                          \
+        B200_REQUIRE(false, "b200_ln_gate: unsupported dtype combination y=%d z=%d out=%d", y_dtype, z_dtype, out_dtype); \
     } while (0)
 
 }  // namespace b200
@@ -201,7 +206,7 @@ using namespace b200;
 
 extern "C" int b200_ln_gate_grid(int64_t rows) { return lg_grid(rows); }
 
-extern "C" int b200_ln_gate_fwd(const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
+extern "C" int b200_ln_gate_fwd(const void* y, int32_t y_dtype, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype, const float* w,
                                 const float* b, void* out, int32_t out_dtype, float* mean, float* rstd, int64_t rows, int32_t D, float eps,
                                 b200_stream_t stream) {
     B200_REQUIRE(y && w && b && out && mean && rstd, "b200_ln_gate_fwd: NULL argument");
@@ -212,8 +217,8 @@ extern "C" int b200_ln_gate_fwd(const float* y, int64_t y_row_stride, const void
     LG_DISPATCH(lg_fwd_launch, y, y_row_stride, z, z_row_stride, w, b, out, mean, rstd, rows, D, eps, st);
 }
 
-extern "C" int b200_ln_gate_bwd(const void* dout, const float* y, int64_t y_row_stride, const void* z, int64_t z_row_stride, int32_t z_dtype,
-                                const float* w, const float* b, int32_t out_dtype, const float* mean, const float* rstd, float* dy, void* dz,
+extern "C" int b200_ln_gate_bwd(const void* dout, const void* y, int32_t y_dtype, int64_t y_row_stride, const void* z, int64_t z_row_stride,
+                                int32_t z_dtype, const float* w, const float* b, int32_t out_dtype, const float* mean, const float* rstd, void* dy, void* dz,
                                 float* dw_partial, float* db_partial, int64_t rows, int32_t D, b200_stream_t stream) {
     B200_REQUIRE(dout && y && w && b && mean && rstd && dy && dw_partial && db_partial, "b200_ln_gate_bwd: NULL argument");
     B200_REQUIRE((z == nullptr) == (dz == nullptr), "b200_ln_gate_bwd: dz must be given exactly when z is");

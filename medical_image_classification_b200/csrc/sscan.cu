@@ -167,6 +167,50 @@ __device__ __forceinline__ void stage16(const Stager& s, unsigned stage_off, int
     cp_async16_s(s.dst + stage_off, ok ? s.src + l : s.src, ok, ca);
 }
 
+// ---- 16-bit I/O: the same double-buffered pipeline with one 8-byte cp.async (4 elements) per lane and tile.  Tiles stay
+// 16-bit in shared memory, [16 rows or states][8 steps] with a 16-byte pitch: the activation tile in the first half of its
+// fp32 slot, the B / C tiles in the second halves of slots 0 / 1 (converted to the fp32 B / C tiles once per chunk).
+struct Stager16 {
+    const char* src;
+    unsigned dst;
+    bool ok;
+};
+template <typename T>
+__device__ __forceinline__ Stager16 make_stager16(float* slot, int elem_off, const T* base, int64_t stride, int nvalid, int lane) {
+    const int r = lane >> 1, c = (lane & 1) * 4;
+    Stager16 s;
+    s.ok = r < nvalid;
+    s.src = reinterpret_cast<const char*>(base + (s.ok ? (size_t)r * stride : 0));
+    s.dst = smem_u32(reinterpret_cast<T*>(slot) + elem_off + r * TC + c);
+    return s;
+}
+__device__ __forceinline__ void stage8(const Stager16& s, unsigned stage_off, int l, int L) {
+    const bool ok = s.ok && (unsigned)l < (unsigned)L;
+    const int n = ok ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s.dst + stage_off), "l"(ok ? s.src + 2 * (size_t)l : s.src), "r"(n)
+                 : "memory");
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(unsigned w) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    } else {
+        return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    }
+}
+// rows i and i + 8, columns c0 and c0 + 1 of a staged 16-bit activation tile
+template <typename T> __device__ __forceinline__ void read_rows16(const float* slot, int i, int sq, float (&a)[2], float (&b)[2]) {
+    const unsigned* w = reinterpret_cast<const unsigned*>(slot);
+    const float2 va = unpack2<T>(w[i * 4 + sq]), vb = unpack2<T>(w[(i + 8) * 4 + sq]);
+    a[0] = va.x; a[1] = va.y; b[0] = vb.x; b[1] = vb.y;
+}
+// staged 16-bit B or C tile (second half of a raw slot) -> fp32 tile in the bc_pos layout; 4 elements per lane
+template <typename T> __device__ __forceinline__ void convert_bc16(float* tile, const float* slot, int lane) {
+    const int n = lane >> 1, c = (lane & 1) * 4;
+    const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const T*>(slot) + TR * TC + n * TC + c);
+    const float2 lo = unpack2<T>(w.x), hi = unpack2<T>(w.y);
+    *reinterpret_cast<float4*>(tile + bc_pos(n, c)) = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // Element-wise fallbacks (L % 4 != 0 or unaligned views): column c <-> sequence position l_lo + c; out-of-range -> 0.
 __device__ __forceinline__ void stage_rows_slow(float* tile, const float* base, int64_t row_stride, int nrows, int l_lo, int L, int lane) {
 #pragma unroll 1
@@ -215,8 +259,8 @@ __device__ __forceinline__ void stage_ckpt(float* tile, const float* src, int la
 template <typename T>
 __device__ __forceinline__ bool can_vectorize(const void* p, int64_t row_stride, int64_t batch_stride, int64_t group_stride,
                                               int L) {
-    return sizeof(T) == 4 && (L & 3) == 0 && (row_stride & 3) == 0 && (batch_stride & 3) == 0 && (group_stride & 3) == 0 &&
-           (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    return (L & 3) == 0 && (row_stride & 3) == 0 && (batch_stride & 3) == 0 && (group_stride & 3) == 0 &&
+           (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0;   // 4 elements per cp.async: 16 bytes fp32, 8 bytes 16-bit
 }
 
 // two adjacent sequence positions of one row
@@ -352,12 +396,26 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
     const Stager sd = make_row_stager(sm.raw[0][1], (const float*)d_base, p.delta_row_stride, t.nrows, lane);
     const Stager sB = make_bc_stager(sm.bc[0][0], (const float*)B_base, p.B_state_stride, N, lane);
     const Stager sC = make_bc_stager(sm.bc[0][1], (const float*)C_base, p.C_state_stride, N, lane);
+    Stager16 hu, hd, hB, hC;
+    if constexpr (!ASYNC) {
+        hu = make_stager16<T>(sm.raw[0][0], 0, u_base, p.u_row_stride, t.nrows, lane);
+        hd = make_stager16<T>(sm.raw[0][1], 0, d_base, p.delta_row_stride, t.nrows, lane);
+        hB = make_stager16<T>(sm.raw[0][0], TR * TC, B_base, p.B_state_stride, N, lane);
+        hC = make_stager16<T>(sm.raw[0][1], TR * TC, C_base, p.C_state_stride, N, lane);
+    }
     const int lc = (lane & 1) * 4;
     auto prefetch = [&](int c) {
-        if (ASYNC) {
+        if (ASYNC || fast) {
             if (c < nck) {
                 const int buf = c & 1, l_lo = l_lo_of(c);
-                if (fast) {
+                if constexpr (!ASYNC) {
+                    const int l = l_lo + lc;
+                    const unsigned off = buf * (unsigned)sizeof(sm.raw[0]);
+                    stage8(hu, off, l, L);
+                    stage8(hd, off, l, L);
+                    stage8(hB, off, l, L);
+                    stage8(hC, off, l, L);
+                } else if (fast) {
                     const int l = l_lo + lc;
                     if (tma) {
                         if (lane == 0) {
@@ -410,6 +468,13 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
             const float2 db = *reinterpret_cast<const float2*>(&sm.raw[buf][1][raw_pos(i + 8, c0)]);
             uA[0] = ua.x; uA[1] = ua.y; uB[0] = ub.x; uB[1] = ub.y;
             dlA[0] = da.x; dlA[1] = da.y; dlB[0] = db.x; dlB[1] = db.y;
+        } else if (fast) {
+            cp_async_wait<1>();
+            __syncwarp();
+            read_rows16<T>(sm.raw[buf][0], i, sq, uA, uB);
+            read_rows16<T>(sm.raw[buf][1], i, sq, dlA, dlB);
+            convert_bc16<T>(sm.bc[buf][0], sm.raw[buf][0], lane);
+            convert_bc16<T>(sm.bc[buf][1], sm.raw[buf][1], lane);
         } else {
             fill_bc_sync<T>(sm.bc[buf][0], B_base, p.B_state_stride, N, l_lo, L, lane);
             fill_bc_sync<T>(sm.bc[buf][1], C_base, p.C_state_stride, N, l_lo, L, lane);
@@ -481,7 +546,7 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
         __syncwarp();  // every lane is done with this chunk's tiles
         prefetch(c + 2);
     }
-    if (ASYNC) cp_async_wait<0>();
+    if (ASYNC || fast) cp_async_wait<0>();
     if (p.last_state != nullptr) {
 #pragma unroll
         for (int j = 0; j < SPT; ++j) {
@@ -579,6 +644,14 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     const Stager sg = make_row_stager(sm.raw[0][2], (const float*)g_base, q.dout_row_stride, t.nrows, lane);
     const Stager sB = make_bc_stager(sm.bc[0][0], (const float*)B_base, p.B_state_stride, N, lane);
     const Stager sC = make_bc_stager(sm.bc[0][1], (const float*)C_base, p.C_state_stride, N, lane);
+    Stager16 hu, hd, hg, hB, hC;
+    if constexpr (!ASYNC) {
+        hu = make_stager16<T>(sm.raw[0][0], 0, u_base, p.u_row_stride, t.nrows, lane);
+        hd = make_stager16<T>(sm.raw[0][1], 0, d_base, p.delta_row_stride, t.nrows, lane);
+        hg = make_stager16<T>(sm.raw[0][2], 0, g_base, q.dout_row_stride, t.nrows, lane);
+        hB = make_stager16<T>(sm.raw[0][0], TR * TC, B_base, p.B_state_stride, N, lane);
+        hC = make_stager16<T>(sm.raw[0][1], TR * TC, C_base, p.C_state_stride, N, lane);
+    }
     const int lc = (lane & 1) * 4;
     const bool rev = t.rev;
     const int st0 = rev ? TC - 1 - c0 : c0, st1 = rev ? TC - 2 - c0 : c0 + 1;  // scan steps of this lane's two columns
@@ -586,6 +659,17 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
     auto prefetch = [&](int c) {  // chunk c (scan order); chunks are visited last -> first
         if (c >= 0) {
             const int buf = c & 1, l_lo = l_lo_of(c);
+            if constexpr (!ASYNC) {
+                if (fast) {
+                    const int l = l_lo + lc;
+                    const unsigned off = buf * (unsigned)sizeof(sm.raw[0]);
+                    stage8(hu, off, l, L);
+                    stage8(hd, off, l, L);
+                    stage8(hg, off, l, L);
+                    stage8(hB, off, l, L);
+                    stage8(hC, off, l, L);
+                }
+            }
             if (ASYNC) {
                 if (fast) {
                     const int l = l_lo + lc;
@@ -647,6 +731,13 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
             uA[0] = ua.x; uA[1] = ua.y; uB[0] = ub.x; uB[1] = ub.y;
             dlA[0] = da.x; dlA[1] = da.y; dlB[0] = db.x; dlB[1] = db.y;
             gA[0] = ga.x; gA[1] = ga.y; gB[0] = gb.x; gB[1] = gb.y;
+        } else if (fast) {
+            read_rows16<T>(sm.raw[buf][0], i, sq, uA, uB);
+            read_rows16<T>(sm.raw[buf][1], i, sq, dlA, dlB);
+            read_rows16<T>(sm.raw[buf][2], i, sq, gA, gB);
+            convert_bc16<T>(sm.bc[buf][0], sm.raw[buf][0], lane);
+            convert_bc16<T>(sm.bc[buf][1], sm.raw[buf][1], lane);
+            __syncwarp();   // the raw slots are reused below for this lane's parked values
         } else {
             fill_bc_sync<T>(sm.bc[buf][0], B_base, p.B_state_stride, N, l_lo, L, lane);
             fill_bc_sync<T>(sm.bc[buf][1], C_base, p.C_state_stride, N, l_lo, L, lane);

@@ -41,8 +41,8 @@ def _layer_norm(x, norm):
     autocast like F.layer_norm's consumer would see it (fp32 without autocast)."""
     if x.is_cuda and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and x.shape[-1] <= 1024 and x.dtype in (torch.float32, torch.bfloat16):
         from .ss2d import LnGateFn
-        x32 = x.to(torch.float32, memory_format=torch.contiguous_format)   # cast + layout in one copy (no-op when already so)
-        return LnGateFn.apply(x32, None, norm.weight, norm.bias, norm.eps, torch.float32)
+        x = x.contiguous()   # rows contiguous (no-op when already so); fp32 or bf16 rows are read as they are
+        return LnGateFn.apply(x, None, norm.weight, norm.bias, norm.eps, torch.float32)
     return norm(x)
 
 
@@ -82,9 +82,10 @@ def channel_shuffle(x, groups: int):
 
 
 class ShuffleCatAddFn(torch.autograd.Function):
-    """out (B, H, W, 2c) fp32 = channel_shuffle(cat(left^T, x), 2) + input with left the conv branch's (B, c, H, W)
+    """out (B, H, W, 2c) = channel_shuffle(cat(left^T, x), 2) + input with left the conv branch's (B, c, H, W)
     output -- NCHW planes or torch.channels_last -- and x (B, H, W, c) channels-last (csrc/glue.cu) -- reference
-    MedMamba.py:486-499, 533-538."""
+    MedMamba.py:486-499, 533-538.  out has torch's promoted dtype: fp32 for an fp32 residual stream, bf16 when the
+    stream and both branches are bf16 (stages 1-3 of an autocast model)."""
 
     @staticmethod
     def forward(ctx, left, x, inp):
@@ -95,25 +96,28 @@ class ShuffleCatAddFn(torch.autograd.Function):
         cl = left.is_contiguous(memory_format=torch.channels_last) and not left.is_contiguous()
         if not cl:
             left = left.contiguous()
+        if inp.dtype == torch.bfloat16 and left.dtype != torch.bfloat16:
+            inp = inp.float()                                  # torch would promote the sum to fp32
         x, inp = x.to(left.dtype).contiguous(), inp.contiguous()
-        out = torch.empty((B, H, W, 2 * c), dtype=torch.float32, device=inp.device)
+        out = torch.empty((B, H, W, 2 * c), dtype=inp.dtype, device=inp.device)
         with torch.cuda.device(inp.device):
             _lib.check(lib.b200_shuffle_cat_add_fwd(left.data_ptr(), int(cl), x.data_ptr(), _lib.dtype_code(left.dtype), inp.data_ptr(),
-                                                    out.data_ptr(), B, c, H * W, _lib.stream_ptr(inp.device)), "b200_shuffle_cat_add_fwd")
-        ctx.meta = (B, c, H, W, left.dtype, cl)
+                                                    out.data_ptr(), _lib.dtype_code(inp.dtype), B, c, H * W, _lib.stream_ptr(inp.device)),
+                       "b200_shuffle_cat_add_fwd")
+        ctx.meta = (B, c, H, W, left.dtype, cl, inp.dtype)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         from . import _lib
         lib = _lib.load()
-        B, c, H, W, ldt, cl = ctx.meta
-        dout = dout.float().contiguous()
+        B, c, H, W, ldt, cl, iodt = ctx.meta
+        dout = dout.to(iodt).contiguous()
         dleft = torch.empty((B, c, H, W), dtype=ldt, device=dout.device, memory_format=torch.channels_last if cl else torch.contiguous_format)
         dx = torch.empty((B, H, W, c), dtype=ldt, device=dout.device)
         with torch.cuda.device(dout.device):
-            _lib.check(lib.b200_shuffle_cat_add_bwd(dout.data_ptr(), dleft.data_ptr(), int(cl), dx.data_ptr(), _lib.dtype_code(ldt), B, c, H * W,
-                                                    _lib.stream_ptr(dout.device)), "b200_shuffle_cat_add_bwd")
+            _lib.check(lib.b200_shuffle_cat_add_bwd(dout.data_ptr(), _lib.dtype_code(iodt), dleft.data_ptr(), int(cl), dx.data_ptr(),
+                                                    _lib.dtype_code(ldt), B, c, H * W, _lib.stream_ptr(dout.device)), "b200_shuffle_cat_add_bwd")
         return dleft, dx, dout
 
 
@@ -142,7 +146,7 @@ class SS_Conv_SSM(nn.Module):
 
     def forward(self, input):
         left, right = input.chunk(2, dim=-1)
-        if right.is_cuda and right.dtype == torch.float32 and isinstance(self.ln_1, nn.LayerNorm) and right.shape[-1] <= 1024:
+        if right.is_cuda and right.dtype in (torch.float32, torch.bfloat16) and isinstance(self.ln_1, nn.LayerNorm) and right.shape[-1] <= 1024:
             from .ss2d import layer_norm_rows
             normed = layer_norm_rows(right, self.ln_1)     # pre-norm, the right half read in place (csrc/lngate.cu)
         else:
@@ -153,7 +157,7 @@ class SS_Conv_SSM(nn.Module):
         left = left.permute(0, 3, 1, 2)
         left = left.contiguous(memory_format=torch.channels_last) if input.is_cuda else left.contiguous()
         left = self.conv33conv33conv11(left)
-        if (input.is_cuda and input.dtype == torch.float32 and left.dtype in (torch.float32, torch.bfloat16)
+        if (input.is_cuda and input.dtype in (torch.float32, torch.bfloat16) and left.dtype in (torch.float32, torch.bfloat16)
                 and x.dtype in (torch.float32, torch.bfloat16) and left.shape[0] <= 65535):
             return ShuffleCatAddFn.apply(left, x, input)   # cat + channel shuffle + residual in one pass (csrc/glue.cu)
         left = left.permute(0, 2, 3, 1)

@@ -78,8 +78,9 @@ def _rows_view(t, D):
 
 class LnGateFn(torch.autograd.Function):
     """out = LayerNorm(y) [* silu(z)] in one pass over HBM (csrc/lngate.cu) -- reference MedMamba.py:478-479 (with z)
-    and the block pre-norm `ln_1` (MedMamba.py:531, z = None).  y (..., D) fp32, z (..., D) fp32 / bf16; both may be
-    strided views with contiguous rows (halves of a chunk) and are read in place; returns out_dtype."""
+    and the block pre-norm `ln_1` (MedMamba.py:531, z = None).  y (..., D) fp32 (or bf16 when z is None: the bf16 residual
+    stream of an autocast model), z (..., D) fp32 / bf16; both may be strided views with contiguous rows (halves of a
+    chunk) and are read in place; returns out_dtype; dy comes back in y's dtype."""
 
     @staticmethod
     def forward(ctx, y, z, weight, bias, eps, out_dtype):
@@ -87,7 +88,7 @@ class LnGateFn(torch.autograd.Function):
         _lib.require_cuda(y, z, weight, bias)
         lib = _lib.load()
         D = y.shape[-1]
-        if y.dtype != torch.float32:
+        if y.dtype != torch.float32 and not (y.dtype == torch.bfloat16 and z is None):
             y = y.float()
         y2, ys = _rows_view(y, D)
         z2, zs = (None, 0)
@@ -102,7 +103,7 @@ class LnGateFn(torch.autograd.Function):
         rstd = torch.empty(rows, dtype=torch.float32, device=y.device)
         zcode = _lib.dtype_code(z2.dtype) if z2 is not None else 0
         with torch.cuda.device(y.device):
-            _lib.check(lib.b200_ln_gate_fwd(y2.data_ptr(), ys, _lib.ptr(z2), zs, zcode, w32.data_ptr(), b32.data_ptr(), out.data_ptr(),
+            _lib.check(lib.b200_ln_gate_fwd(y2.data_ptr(), _lib.dtype_code(y2.dtype), ys, _lib.ptr(z2), zs, zcode, w32.data_ptr(), b32.data_ptr(), out.data_ptr(),
                                             _lib.dtype_code(out_dtype), mean.data_ptr(), rstd.data_ptr(), rows, D, float(eps),
                                             _lib.stream_ptr(y.device)), "b200_ln_gate_fwd")
         ctx.save_for_backward(y2, z2, w32, b32, mean, rstd)
@@ -118,13 +119,13 @@ class LnGateFn(torch.autograd.Function):
         rows, D = ctx.rows, ctx.shape[-1]
         dout = dout.reshape(rows, D).contiguous()
         dev = dout.device
-        dy = torch.empty((rows, D), dtype=torch.float32, device=dev)
+        dy = torch.empty((rows, D), dtype=y2.dtype, device=dev)
         dz = torch.empty((rows, D), dtype=z2.dtype, device=dev) if z2 is not None else None
         grid = lib.b200_ln_gate_grid(rows)
         part = torch.empty((2, grid, D), dtype=torch.float32, device=dev)
         zcode = _lib.dtype_code(z2.dtype) if z2 is not None else 0
         with torch.cuda.device(dev):
-            _lib.check(lib.b200_ln_gate_bwd(dout.data_ptr(), y2.data_ptr(), ctx.ys, _lib.ptr(z2), ctx.zs, zcode, w32.data_ptr(), b32.data_ptr(),
+            _lib.check(lib.b200_ln_gate_bwd(dout.data_ptr(), y2.data_ptr(), _lib.dtype_code(y2.dtype), ctx.ys, _lib.ptr(z2), ctx.zs, zcode, w32.data_ptr(), b32.data_ptr(),
                                             _lib.dtype_code(dout.dtype), mean.data_ptr(), rstd.data_ptr(), dy.data_ptr(), _lib.ptr(dz),
                                             part[0].data_ptr(), part[1].data_ptr(), rows, D, _lib.stream_ptr(dev)), "b200_ln_gate_bwd")
         dwb = part.sum(1)

@@ -17,7 +17,8 @@ def ref(left, x, inp):
 @pytest.mark.parametrize("shape", [(2, 48, 56, 56), (3, 96, 28, 28), (2, 384, 7, 7), (1, 20, 5, 9), (2, 33, 3, 2)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("channels_last", [False, True])
-def test_shuffle_cat_add_bit_exact(shape, dtype, channels_last):
+@pytest.mark.parametrize("stream_dtype", [torch.float32, torch.bfloat16])
+def test_shuffle_cat_add_bit_exact(shape, dtype, channels_last, stream_dtype):
     from medical_image_classification_b200.models import ShuffleCatAddFn
     B, c, H, W = shape
     dev = "cuda"
@@ -27,7 +28,7 @@ def test_shuffle_cat_add_bit_exact(shape, dtype, channels_last):
         left = left.contiguous(memory_format=torch.channels_last)
     left.requires_grad_()
     x = torch.randn(B, H, W, c, device=dev, dtype=dtype).requires_grad_()
-    inp = torch.randn(B, H, W, 2 * c, device=dev).requires_grad_()
+    inp = torch.randn(B, H, W, 2 * c, device=dev, dtype=stream_dtype).requires_grad_()   # bf16: stages 1-3 under autocast
     out = ShuffleCatAddFn.apply(left, x, inp)
     g = torch.randn_like(out)
     out.backward(g)
@@ -36,6 +37,6 @@ def test_shuffle_cat_add_bit_exact(shape, dtype, channels_last):
         t.grad = None
     o2 = ref(left, x, inp)
     o2.backward(g)
-    assert out.dtype == torch.float32 and torch.equal(out, o2)
+    assert out.dtype == o2.dtype and torch.equal(out, o2)   # torch's promoted dtype: bf16 only when all three are bf16
     for a, t in zip(got, (left, x, inp)):
         assert torch.equal(a, t.grad)

@@ -87,3 +87,32 @@ def test_plain_layer_norm_on_strided_half(D, odt):
     assert relerr(out, o2) < ftol
     for name, a, c in zip(("dinput", "dw", "db"), got, (inp.grad, w.grad, b.grad)):
         assert relerr(a, c) < btol, name
+
+
+@pytest.mark.parametrize("D", [96, 192, 384, 768])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_plain_layer_norm_of_bf16_rows(D, odt):
+    """bf16 y (the residual stream of an autocast model after PatchMerging's Linear), z = None: rows are read as bf16 and
+    dy comes back in bf16 -- equal to F.layer_norm of the upcast rows (what autocast runs) up to the output rounding."""
+    from medical_image_classification_b200.ss2d import LnGateFn
+    dev = "cuda"
+    torch.manual_seed(D + 2)
+    inp = (1.5 * torch.randn(2, 9, 10, 2 * D, device=dev) - 0.3).to(torch.bfloat16).requires_grad_()
+    right = inp.chunk(2, dim=-1)[1]
+    w = (1.0 + 0.1 * torch.randn(D, device=dev)).requires_grad_()
+    b = (0.1 * torch.randn(D, device=dev)).requires_grad_()
+    out = LnGateFn.apply(right, None, w, b, 1e-6, odt)
+    assert out.dtype == odt
+    g = torch.randn_like(out)
+    out.backward(g)
+    got = [t.grad.clone() for t in (inp, w, b)]
+    assert got[0].dtype == torch.bfloat16
+    for t in (inp, w, b):
+        t.grad = None
+    o2 = torch.nn.functional.layer_norm(inp.chunk(2, dim=-1)[1].float(), (D,), w, b, 1e-6)
+    o2.backward(g.float())
+    assert relerr(out, o2) < (2e-6 if odt == torch.float32 else 4e-3)
+    assert relerr(got[0][..., D:], inp.grad[..., D:]) < 8e-3          # bf16 rounding of dy
+    assert float(got[0][..., :D].abs().max()) == 0.0
+    assert relerr(got[1], w.grad) < (2e-5 if odt == torch.float32 else 1e-2)
+    assert relerr(got[2], b.grad) < (2e-5 if odt == torch.float32 else 1e-2)
