@@ -118,7 +118,7 @@ class ScanProfiler:
         """s = bytes per I/O element, E = B*KD*L, Ebc = B*K*N*L.
         fwd: s*(3E + 2Ebc) + 4*(KD*N + 2KD);  bwd: s*(5E + 2Ebc) + 4*2Ebc + 4*(2KD*N + 4KD)."""
         s = u.element_size()
-        batch, KD, L = delta.shape
+        batch, KD, L = delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), delta.shape[-1]   # (B, KD, L) or a (B, K, D, L) view
         G, N = Bm.shape[1], Bm.shape[2]
         E, Ebc = batch * KD * L, batch * G * N * L
         if kind == "fwd":
@@ -140,7 +140,7 @@ class ScanProfiler:
             return
         e1 = self.torch.cuda.Event(enable_timing=True)
         e1.record()
-        key = (kind, tuple(delta.shape), Bm.shape[2], str(u.dtype))
+        key = (kind, (delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), delta.shape[-1]), Bm.shape[2], str(u.dtype))
         self.records.append((key, self.algorithmic_bytes(kind, u, delta, Bm), e0, e1))
 
     def summary(self, peak_gbs, peak_src, steps):

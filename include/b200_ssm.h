@@ -54,6 +54,9 @@ typedef enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2 } b200_dtype;
  *     (directions k and k+2 scan the same image in opposite orders).  u is then addressed as
  *       u + b*u_batch_stride + (g / u_group_div)*u_group_stride + r*u_row_stride,  r = d % (dim/G).
  *     Plain operator: u_group_div = 1, u_group_stride = (dim/G)*u_row_stride.
+ *     delta (and ddelta) are addressed the same way with their own strides and no sharing:
+ *       delta + b*delta_batch_stride + g*delta_group_stride + r*delta_row_stride
+ *     (plain operator: delta_group_stride = (dim/G)*delta_row_stride).
  *
  * State checkpoints (replace the reference's chunk tensor `x`, selective_scan.cpp:313): the
  * forward writes the state entering every `ckpt_every`-th step into `ckpt`, laid out
@@ -70,7 +73,7 @@ typedef struct {
     int32_t u_group_div;
     int32_t ckpt_every;     /* 8; ignored when ckpt == NULL */
     int64_t u_batch_stride, u_group_stride, u_row_stride;
-    int64_t delta_batch_stride, delta_row_stride;
+    int64_t delta_batch_stride, delta_group_stride, delta_row_stride; /* addressed like u (group g, row r of the group) */
     int64_t B_batch_stride, B_group_stride, B_state_stride;
     int64_t C_batch_stride, C_group_stride, C_state_stride;
     int64_t z_batch_stride, z_row_stride;
@@ -97,15 +100,19 @@ typedef struct {
     int64_t dout_batch_stride, dout_group_stride, dout_row_stride;
     int64_t dout_group_div;
     int64_t du_batch_stride, du_row_stride;
-    int64_t ddelta_batch_stride, ddelta_row_stride;
+    int64_t ddelta_batch_stride, ddelta_group_stride, ddelta_row_stride;
+    int64_t dB_batch_stride, dB_group_stride, dB_state_stride;
+    int64_t dC_batch_stride, dC_group_stride, dC_state_stride;
     int64_t dz_batch_stride, dz_row_stride;
     const void* dout; /* (batch, dim, L) io_dtype */
     void* du;         /* (batch, dim, L) io_dtype: one row per (b, d) even when u rows are shared */
     void* ddelta;     /* (batch, dim, L) io_dtype */
     void* dz;         /* (batch, dim, L) io_dtype, required iff f.z != NULL */
     /* The next five are ACCUMULATED with fp32 atomics (like selective_scan.cpp:460-466):
-       the caller zero-fills them first.  dB/dC are contiguous (batch, G, N, L) f32 whatever
-       io_dtype is (selective_scan.cpp:461-462). */
+       the caller zero-fills them first.  dB/dC are (batch, G, N, L) f32 whatever io_dtype is
+       (selective_scan.cpp:461-462), rows of L contiguous, addressed through their strides (contiguous:
+       G*N*L, N*L, L) -- like delta / ddelta they may live inside a wider buffer (SS2D keeps B, C, delta of all
+       four directions in ONE projection output and their gradients in one buffer of the same layout). */
     float* dA;          /* (dim, N) */
     float* dB;
     float* dC;
@@ -117,6 +124,19 @@ size_t b200_sscan_ckpt_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t
                              int32_t n_groups, int32_t ckpt_every);
 int b200_sscan_fwd(const b200_sscan_fwd_params* p, b200_stream_t stream);
 int b200_sscan_bwd(const b200_sscan_bwd_params* p, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Strided twins of the cross-scan pack for the fused SS2D core (medical_image_classification_b200/cross.py::SS2DCoreFn;
+ * reference MedMamba.py:393-400): x2 is addressed as x2 + b*batch_stride + i*layout_stride + d*row_stride (i = 0 row-major
+ * plane, 1 column-major plane; rows of L contiguous), so that it can live in the (2, D, B, L) layout in which the x_proj /
+ * dt_proj contraction is one GEMM over B*L columns.  b200_cross_scan_unpack4 is the whole adjoint in one pass:
+ * dx (B, D, H, W) = du[b,0,d] + du[b,1,d] + gx2[b,0,d] + (du[b,2,d] + du[b,3,d] + gx2[b,1,d])^T with du (B, 4, D, L) contiguous
+ * (the scan's du per direction: hw, hw reversed, wh, wh reversed, all at memory positions) and gx2 laid out like x2.  f32.
+ * ------------------------------------------------------------------------------------------ */
+int b200_cross_scan_pack_strided(const float* x, float* x2, int64_t x2_batch_stride, int64_t x2_layout_stride, int64_t x2_row_stride,
+                                 int32_t batch, int32_t D, int32_t H, int32_t W, b200_stream_t stream);
+int b200_cross_scan_unpack4(const float* du, const float* gx2, int64_t x2_batch_stride, int64_t x2_layout_stride, int64_t x2_row_stride,
+                            float* dx, int32_t batch, int32_t D, int32_t H, int32_t W, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * SS2D cross-scan / cross-merge helpers (reference MedMamba.py:393-395, 420-424, 476-477).

@@ -23,7 +23,7 @@ class SScanFwdParams(C.Structure):
         ("batch", i32), ("dim", i32), ("seqlen", i32), ("dstate", i32), ("n_groups", i32),
         ("io_dtype", i32), ("delta_softplus", i32), ("rev_mask", u32), ("u_group_div", i32), ("ckpt_every", i32),
         ("u_batch_stride", i64), ("u_group_stride", i64), ("u_row_stride", i64),
-        ("delta_batch_stride", i64), ("delta_row_stride", i64),
+        ("delta_batch_stride", i64), ("delta_group_stride", i64), ("delta_row_stride", i64),
         ("B_batch_stride", i64), ("B_group_stride", i64), ("B_state_stride", i64),
         ("C_batch_stride", i64), ("C_group_stride", i64), ("C_state_stride", i64),
         ("z_batch_stride", i64), ("z_row_stride", i64),
@@ -39,7 +39,9 @@ class SScanBwdParams(C.Structure):
         ("f", SScanFwdParams),
         ("dout_batch_stride", i64), ("dout_group_stride", i64), ("dout_row_stride", i64), ("dout_group_div", i64),
         ("du_batch_stride", i64), ("du_row_stride", i64),
-        ("ddelta_batch_stride", i64), ("ddelta_row_stride", i64),
+        ("ddelta_batch_stride", i64), ("ddelta_group_stride", i64), ("ddelta_row_stride", i64),
+        ("dB_batch_stride", i64), ("dB_group_stride", i64), ("dB_state_stride", i64),
+        ("dC_batch_stride", i64), ("dC_group_stride", i64), ("dC_state_stride", i64),
         ("dz_batch_stride", i64), ("dz_row_stride", i64),
         ("dout", vp), ("du", vp), ("ddelta", vp), ("dz", vp),
         ("dA", vp), ("dB", vp), ("dC", vp), ("dD", vp), ("ddelta_bias", vp),
@@ -78,6 +80,7 @@ EXPORTS = [
     "b200_cross_scan4", "b200_cross_scan4_bwd", "b200_ssd_merge4", "b200_ssd_merge4_bwd",
     "b200_ssd_workspace_bytes", "b200_ssd_bwd_scratch_bytes", "b200_ssd_fwd", "b200_ssd_bwd",
     "b200_rmsnorm_gated_fwd", "b200_rmsnorm_gated_bwd",
+    "b200_cross_scan_pack_strided", "b200_cross_scan_unpack4",
     "b200_ln_gate_grid", "b200_ln_gate_fwd", "b200_ln_gate_bwd",
     "b200_dwconv_silu_fwd", "b200_dwconv_silu_bwd",
     "b200_shuffle_cat_add_fwd", "b200_shuffle_cat_add_bwd",
@@ -128,6 +131,8 @@ def load() -> C.CDLL:
     lib.b200_dwconv_silu_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_shuffle_cat_add_fwd.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_shuffle_cat_add_bwd.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]
+    lib.b200_cross_scan_pack_strided.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
+    lib.b200_cross_scan_unpack4.argtypes = [vp, vp, i64, i64, i64, vp, i32, i32, i32, i32, vp]
     lib.b200_ln_gate_grid.argtypes = [i64]
     lib.b200_ln_gate_fwd.argtypes = [vp, i32, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, i64, i32, f32, vp]
     lib.b200_ln_gate_bwd.argtypes = [vp, vp, i32, i64, vp, i64, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, vp]

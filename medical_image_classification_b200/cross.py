@@ -125,6 +125,121 @@ class ScanMergeFn(torch.autograd.Function):
                 dbias.to(ctx.dtypes[2]), None, None)
 
 
+class _Tf32:
+    """torch.backends.cuda.matmul.allow_tf32 for the duration of a with-block."""
+
+    def __init__(self, on):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        if self.on:
+            torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+def _weight_grad_splitk(g_big, x2m):
+    """dW (2, 2M, D) = g_big (2, 2M, B*L) @ x2m (2, D, B*L)^T.  The output is a handful of tiles while K = B*L is ~200 K, so
+    K is split across the batch dimension of a strided bmm (views only, no copies) and the partials are summed."""
+    _, M2, BL = g_big.shape
+    D = x2m.shape[1]
+    tiles = 2 * ((M2 + 127) // 128) * ((D + 63) // 64)
+    S = 1
+    while tiles * S < 592 and BL % (2 * S) == 0 and BL // (2 * S) >= 448:
+        S *= 2
+    if S == 1:
+        return torch.bmm(g_big, x2m.transpose(1, 2))
+    Kp = BL // S
+    parts = []
+    for i in range(2):
+        a = g_big[i].view(M2, S, Kp).permute(1, 0, 2)                  # (S, 2M, K')
+        b = x2m[i].view(D, S, Kp).permute(1, 2, 0)                     # (S, K', D)
+        parts.append(torch.bmm(a, b).sum(0))
+    return torch.stack(parts)
+
+
+class SS2DCoreFn(torch.autograd.Function):
+    """The whole SS2D core -- cross-scan, x_proj / dt_proj, four-direction selective scan, cross-merge (reference
+    MedMamba.py:386-424, 476-477) -- as ONE autograd node, so that every intermediate lives in a layout of our choosing:
+
+      x (B, D, H, W) fp32 --pack--> x2 (2, D, B, L)                          [row-major planes | column-major planes]
+      big (2, 2M, B*L) = W_all (2, 2M, D) @ x2 (2, D, B*L)                   ONE batched GEMM with B*L columns
+         W_all[k] (M = 2N + D rows) = [x_proj rows of B ; of C ; dt_proj_weight @ x_proj rows of dt]   (internal direction
+         order; the rank-R dt projection is folded into the same GEMM, so `delta` comes out of it directly)
+      scan reads B, C, delta as strided views of `big`, u as a view of x2   (b200_sscan_* take arbitrary leading strides)
+      y (B, L, D) = cross-merge of the four direction outputs.
+
+    Backward: the scan kernel writes ddelta and accumulates dB, dC straight into `g_big` (the layout of `big`), so
+    dW_all = g_big @ x2^T and gx2 = W_all^T @ g_big are two GEMMs over K resp. N = B*L with no per-sample partials, no
+    slice / cat / add kernels; dx = b200_cross_scan_unpack4(du, gx2) finishes the adjoint of the cross-scan in one pass.
+    tf32: run the three GEMMs in TF32 (used under autocast, where the reference runs these einsums in bf16)."""
+
+    @staticmethod
+    def forward(ctx, x, W_all, A, Ds, delta_bias, N, tf32):
+        _lib.require_cuda(x, W_all, A, Ds, delta_bias)
+        lib = _lib.load()
+        x = x.float().contiguous()
+        B, D, H, W = x.shape
+        L = H * W
+        M = W_all.shape[1]
+        assert W_all.shape == (4, M, D) and M == 2 * N + D
+        dev = x.device
+        x2 = torch.empty((2, D, B, L), dtype=torch.float32, device=dev)
+        strides = (L, D * B * L, B * L)                               # (batch, layout, row) element strides of x2
+        with torch.cuda.device(dev):
+            _lib.check(lib.b200_cross_scan_pack_strided(x.data_ptr(), x2.data_ptr(), *strides, B, D, H, W, _lib.stream_ptr(dev)),
+                       "b200_cross_scan_pack_strided")
+        Wm = W_all.detach().float().reshape(2, 2 * M, D).contiguous()
+        with _Tf32(tf32):
+            big = torch.bmm(Wm, x2.view(2, D, B * L))                  # (2, 2M, B*L)
+        big4 = big.view(4, M, B, L).permute(2, 0, 1, 3)                # (B, 4, M, L) view
+        A32, D32, b32 = _f32c(A), _f32c(Ds), _f32c(delta_bias)
+        need_grad = any(ctx.needs_input_grad)
+        ys, _, ckpt = launch_fwd(x2.permute(2, 0, 1, 3), big4[:, :, 2 * N:], A32, big4[:, :, :N], big4[:, :, N:2 * N], D32, None, b32,
+                                 True, REV_MASK, 2, want_ckpt=need_grad)
+        y = torch.empty((B, L, D), dtype=torch.float32, device=dev)
+        _plane_op("b200_cross_merge", ys, y, B, D, H, W)
+        if need_grad:
+            ctx.save_for_backward(x2, big, Wm, A32, D32, b32, ckpt)
+        ctx.meta = (B, D, H, W, M, N, bool(tf32))
+        ctx.dtypes = (W_all.dtype, A.dtype, Ds.dtype, delta_bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, big, Wm, A32, D32, b32, ckpt = ctx.saved_tensors
+        B, D, H, W, M, N, tf32 = ctx.meta
+        L = H * W
+        lib = _lib.load()
+        dev = dy.device
+        dy = dy.contiguous().float()
+        d2 = torch.empty((B, 2 * D, L), dtype=torch.float32, device=dev)
+        _plane_op("b200_cross_merge_bwd", dy, d2, B, D, H, W)
+        big4 = big.view(4, M, B, L).permute(2, 0, 1, 3)
+        g_big = torch.empty_like(big)
+        g4 = g_big.view(4, M, B, L).permute(2, 0, 1, 3)                # (B, 4, M, L) view, like big4
+        g_big.view(4, M, B * L)[:, :2 * N].zero_()                     # dB, dC are accumulated with atomics; ddelta is written
+        du, _, dA, _, _, dD, dbias, _ = launch_bwd(x2.permute(2, 0, 1, 3), big4[:, :, 2 * N:], A32, big4[:, :, :N], big4[:, :, N:2 * N],
+                                                   D32, None, b32, True, ckpt, d2, REV_MASK, 2, 2, True, True,
+                                                   ddelta=g4[:, :, 2 * N:], dB=g4[:, :, :N], dC=g4[:, :, N:2 * N])
+        x2m = x2.view(2, D, B * L)
+        with _Tf32(tf32):
+            dW = _weight_grad_splitk(g_big, x2m)                       # (2, 2M, D)
+            gx2 = torch.bmm(Wm.transpose(1, 2), g_big)                 # (2, D, B*L)
+        dx = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.b200_cross_scan_unpack4(du.data_ptr(), gx2.data_ptr(), L, D * B * L, B * L, dx.data_ptr(), B, D, H, W,
+                                                   _lib.stream_ptr(dev)), "b200_cross_scan_unpack4")
+        wdt, adt, ddt, bdt = ctx.dtypes
+        return dx, dW.view(4, M, D).to(wdt), dA.to(adt), dD.to(ddt), dbias.to(bdt), None, None
+
+
+def ss2d_core(x, W_all, A, Ds, delta_bias, N, tf32=False):
+    return SS2DCoreFn.apply(x, W_all, A, Ds, delta_bias, N, tf32)
+
+
 class CrossScan4Fn(torch.autograd.Function):
     """SSD twin of the cross-scan: x (B, C, H, W) fp32 (a channel slice of a wider NCHW tensor is read in place) ->
     x4 (B, 4, C, L) in the reference's direction order (hw, wh, hw reversed, wh reversed; SSD/MedSSD.py:332-336)."""

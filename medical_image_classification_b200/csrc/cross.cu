@@ -285,6 +285,74 @@ static int run_merge(const void* a, void* o, int batch, int D, int H, int W, boo
         default: return fn<__half>(__VA_ARGS__);                 \
     }
 
+
+// ---- strided twins for the fused SS2D core (cross.py::SS2DCoreFn): x2 lives in the layout (2, D, B, L) -- or any other
+//      given by (batch, layout, row) element strides -- so that the x_proj / dt_proj contraction over it is ONE GEMM with
+//      N = B * L columns.  x (B, D, H, W) f32 -> x2[b, 0, d] = plane, x2[b, 1, d] = plane^T.
+__global__ void __launch_bounds__(256) cross_scan_pack_strided_kernel(const float* __restrict__ x, float* __restrict__ x2, int64_t sB, int64_t sI,
+                                                                      int64_t sD, int D, int H, int W) {
+    __shared__ float tile[32][33];
+    const int plane = blockIdx.x;  // b * D + d
+    const int b = plane / D, d = plane % D;
+    const size_t L = (size_t)H * W;
+    const float* src = x + (size_t)plane * L;
+    float* dst0 = x2 + (size_t)b * sB + (size_t)d * sD;
+    float* dst1 = dst0 + sI;
+    const int w0 = blockIdx.y * 32, h0 = blockIdx.z * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int h = h0 + j, w = w0 + tx;
+        if (h < H && w < W) {
+            const float v = __ldcs(src + (size_t)h * W + w);
+            dst0[(size_t)h * W + w] = v;
+            tile[j][tx] = v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int w = w0 + j, h = h0 + tx;
+        if (h < H && w < W) dst1[(size_t)w * H + h] = tile[tx][j];
+    }
+}
+
+// ---- adjoint of the cross-scan for the fused core: dx (B, D, H, W) = du[b,0,d] + du[b,1,d] + gx2[b,0,d]
+//      + (du[b,2,d] + du[b,3,d] + gx2[b,1,d])^T with du (B, 4, D, L) the scan's input gradient per direction (internal order, at
+//      memory positions) and gx2 the projection's input gradient in x2's strided layout: one pass instead of a 4 -> 2 sum,
+//      a gradient accumulation and an un-pack.
+__global__ void __launch_bounds__(256) cross_scan_unpack4_kernel(const float* __restrict__ du, const float* __restrict__ gx2, int64_t sB,
+                                                                 int64_t sI, int64_t sD, float* __restrict__ dx, int D, int H, int W) {
+    __shared__ float tile[32][33];
+    const int plane = blockIdx.x;
+    const int b = plane / D, d = plane % D;
+    const size_t L = (size_t)H * W;
+    const float* u0 = du + ((size_t)b * 4 * D + d) * L;   // direction k at u0 + k * D * L
+    const float* g0 = gx2 + (size_t)b * sB + (size_t)d * sD;
+    const float* g1 = g0 + sI;
+    float* dst = dx + (size_t)plane * L;
+    const int w0 = blockIdx.y * 32, h0 = blockIdx.z * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t DL = (size_t)D * L;
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int w = w0 + j, h = h0 + tx;
+        if (h < H && w < W) {
+            const size_t o = (size_t)w * H + h;
+            tile[tx][j] = __ldcs(u0 + 2 * DL + o) + __ldcs(u0 + 3 * DL + o) + __ldcs(g1 + o);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int h = h0 + j, w = w0 + tx;
+        if (h < H && w < W) {
+            const size_t o = (size_t)h * W + w;
+            __stcs(dst + o, __ldcs(u0 + o) + __ldcs(u0 + DL + o) + __ldcs(g0 + o) + tile[j][tx]);
+        }
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -308,6 +376,23 @@ extern "C" int b200_cross_merge_bwd(const void* dy, void* dys, int32_t batch, in
                                     b200_stream_t stream) {
     if (int rc = check_dims(dy, dys, batch, D, H, W, dtype, "b200_cross_merge_bwd")) return rc;
     DISPATCH(run_merge, dy, dys, batch, D, H, W, true, (cudaStream_t)stream)
+}
+
+extern "C" int b200_cross_scan_pack_strided(const float* x, float* x2, int64_t x2_batch_stride, int64_t x2_layout_stride, int64_t x2_row_stride,
+                                            int32_t batch, int32_t D, int32_t H, int32_t W, b200_stream_t stream) {
+    if (int rc = check_dims(x, x2, batch, D, H, W, B200_F32, "b200_cross_scan_pack_strided")) return rc;
+    B200_REQUIRE(x2_row_stride >= (int64_t)H * W || x2_batch_stride >= (int64_t)H * W, "b200_cross_scan_pack_strided: overlapping rows");
+    dim3 grid(batch * D, (W + 31) / 32, (H + 31) / 32);
+    cross_scan_pack_strided_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x2, x2_batch_stride, x2_layout_stride, x2_row_stride, D, H, W);
+    return check_launch("cross_scan_pack_strided_kernel");
+}
+extern "C" int b200_cross_scan_unpack4(const float* du, const float* gx2, int64_t x2_batch_stride, int64_t x2_layout_stride, int64_t x2_row_stride,
+                                       float* dx, int32_t batch, int32_t D, int32_t H, int32_t W, b200_stream_t stream) {
+    if (int rc = check_dims(du, dx, batch, D, H, W, B200_F32, "b200_cross_scan_unpack4")) return rc;
+    B200_REQUIRE(gx2 != nullptr, "b200_cross_scan_unpack4: gx2 is NULL");
+    dim3 grid(batch * D, (W + 31) / 32, (H + 31) / 32);
+    cross_scan_unpack4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(du, gx2, x2_batch_stride, x2_layout_stride, x2_row_stride, dx, D, H, W);
+    return check_launch("cross_scan_unpack4_kernel");
 }
 
 extern "C" int b200_cross_scan4(const float* x, int64_t x_batch_stride, float* x4, int32_t batch, int32_t C, int32_t H, int32_t W,

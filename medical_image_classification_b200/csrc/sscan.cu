@@ -373,13 +373,14 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
 
     const T* u_base = (const T*)p.u + (size_t)t.b * p.u_batch_stride + (size_t)(t.g / p.u_group_div) * p.u_group_stride +
                       (size_t)t.r0 * p.u_row_stride;
-    const T* d_base = (const T*)p.delta + (size_t)t.b * p.delta_batch_stride + (size_t)t.d0 * p.delta_row_stride;
+    const T* d_base = (const T*)p.delta + (size_t)t.b * p.delta_batch_stride + (size_t)t.g * p.delta_group_stride +
+                      (size_t)t.r0 * p.delta_row_stride;
     T* o_base = (T*)p.out + (size_t)t.b * p.out_batch_stride + (size_t)t.d0 * p.out_row_stride;
     const T* z_base = HAS_Z ? (const T*)p.z + (size_t)t.b * p.z_batch_stride + (size_t)t.d0 * p.z_row_stride : nullptr;
     const T* B_base = (const T*)p.B + (size_t)t.b * p.B_batch_stride + (size_t)t.g * p.B_group_stride;
     const T* C_base = (const T*)p.C + (size_t)t.b * p.C_batch_stride + (size_t)t.g * p.C_group_stride;
     const bool vec_u = can_vectorize<T>(p.u, p.u_row_stride, p.u_batch_stride, p.u_group_stride, L);
-    const bool vec_d = can_vectorize<T>(p.delta, p.delta_row_stride, p.delta_batch_stride, 0, L);
+    const bool vec_d = can_vectorize<T>(p.delta, p.delta_row_stride, p.delta_batch_stride, p.delta_group_stride, L);
     const bool vec_B = can_vectorize<T>(p.B, p.B_state_stride, p.B_batch_stride, p.B_group_stride, L);
     const bool vec_C = can_vectorize<T>(p.C, p.C_state_stride, p.C_batch_stride, p.C_group_stride, L);
     const bool vec_o = pair_vec_ok<T>(p.out, p.out_row_stride, p.out_batch_stride, L);
@@ -614,24 +615,27 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
 
     const T* u_base = (const T*)p.u + (size_t)t.b * p.u_batch_stride + (size_t)(t.g / p.u_group_div) * p.u_group_stride +
                       (size_t)t.r0 * p.u_row_stride;
-    const T* d_base = (const T*)p.delta + (size_t)t.b * p.delta_batch_stride + (size_t)t.d0 * p.delta_row_stride;
+    const T* d_base = (const T*)p.delta + (size_t)t.b * p.delta_batch_stride + (size_t)t.g * p.delta_group_stride +
+                      (size_t)t.r0 * p.delta_row_stride;
     const T* g_base = (const T*)q.dout + (size_t)t.b * q.dout_batch_stride +
                       (size_t)(t.g / (int)q.dout_group_div) * q.dout_group_stride + (size_t)t.r0 * q.dout_row_stride;
     const T* z_base = HAS_Z ? (const T*)p.z + (size_t)t.b * p.z_batch_stride + (size_t)t.d0 * p.z_row_stride : nullptr;
     T* du_base = (T*)q.du + (size_t)t.b * q.du_batch_stride + (size_t)t.d0 * q.du_row_stride;
-    T* dd_base = (T*)q.ddelta + (size_t)t.b * q.ddelta_batch_stride + (size_t)t.d0 * q.ddelta_row_stride;
+    T* dd_base = (T*)q.ddelta + (size_t)t.b * q.ddelta_batch_stride + (size_t)t.g * q.ddelta_group_stride +
+                 (size_t)t.r0 * q.ddelta_row_stride;
     T* dz_base = HAS_Z ? (T*)q.dz + (size_t)t.b * q.dz_batch_stride + (size_t)t.d0 * q.dz_row_stride : nullptr;
     const T* B_base = (const T*)p.B + (size_t)t.b * p.B_batch_stride + (size_t)t.g * p.B_group_stride;
     const T* C_base = (const T*)p.C + (size_t)t.b * p.C_batch_stride + (size_t)t.g * p.C_group_stride;
-    float* dB_base = q.dB + ((size_t)t.b * p.n_groups + t.g) * (size_t)N * L;
-    float* dC_base = q.dC + ((size_t)t.b * p.n_groups + t.g) * (size_t)N * L;
+    float* dB_base = q.dB + (size_t)t.b * q.dB_batch_stride + (size_t)t.g * q.dB_group_stride;
+    float* dC_base = q.dC + (size_t)t.b * q.dC_batch_stride + (size_t)t.g * q.dC_group_stride;
+    const int dBs = (int)q.dB_state_stride, dCs = (int)q.dC_state_stride;   // N * stride < 2^31 (checked on the host)
     const bool vec_u = can_vectorize<T>(p.u, p.u_row_stride, p.u_batch_stride, p.u_group_stride, L);
-    const bool vec_d = can_vectorize<T>(p.delta, p.delta_row_stride, p.delta_batch_stride, 0, L);
+    const bool vec_d = can_vectorize<T>(p.delta, p.delta_row_stride, p.delta_batch_stride, p.delta_group_stride, L);
     const bool vec_g = can_vectorize<T>(q.dout, q.dout_row_stride, q.dout_batch_stride, q.dout_group_stride, L);
     const bool vec_B = can_vectorize<T>(p.B, p.B_state_stride, p.B_batch_stride, p.B_group_stride, L);
     const bool vec_C = can_vectorize<T>(p.C, p.C_state_stride, p.C_batch_stride, p.C_group_stride, L);
     const bool vec_du = pair_vec_ok<T>(q.du, q.du_row_stride, q.du_batch_stride, L);
-    const bool vec_dd = pair_vec_ok<T>(q.ddelta, q.ddelta_row_stride, q.ddelta_batch_stride, L);
+    const bool vec_dd = pair_vec_ok<T>(q.ddelta, q.ddelta_row_stride, q.ddelta_batch_stride, L) && (q.ddelta_group_stride & 1) == 0;
     const bool vec_dz = HAS_Z && pair_vec_ok<T>(q.dz, q.dz_row_stride, q.dz_batch_stride, L);
 
     const int nck = (L + TC - 1) / TC;
@@ -859,9 +863,8 @@ __device__ __forceinline__ void sscan_bwd_body(const b200_sscan_bwd_params& q, c
             const float rC = rs8_rows(vC, lane);
             const int lcol = l_lo + (rev ? TC - 1 - i : i);   // lane i holds scan step i
             if (n < N && (unsigned)lcol < (unsigned)L) {
-                const int off = n * L + lcol;   // N * L < 2^31 (checked on the host)
-                atomicAdd(dB_base + off, rB);
-                atomicAdd(dC_base + off, rC);
+                atomicAdd(dB_base + n * dBs + lcol, rB);
+                atomicAdd(dC_base + n * dCs + lcol, rC);
             }
         }
 
@@ -1028,7 +1031,7 @@ static bool make_fwd_maps(RowMaps* tm, const b200_sscan_fwd_params* p) {
     return make_row_map(&tm->u, p->u, p->seqlen, rpg, p->n_groups / p->u_group_div, p->batch, p->u_row_stride, p->u_group_stride,
                         p->u_batch_stride) &&
            make_row_map(&tm->delta, p->delta, p->seqlen, rpg, p->n_groups, p->batch, p->delta_row_stride,
-                        (int64_t)rpg * p->delta_row_stride, p->delta_batch_stride);
+                        p->delta_group_stride, p->delta_batch_stride);
 }
 
 template <typename T>
@@ -1107,6 +1110,9 @@ extern "C" int b200_sscan_bwd(const b200_sscan_bwd_params* q, b200_stream_t stre
     B200_REQUIRE(q->dout && q->du && q->ddelta && q->dA && q->dB && q->dC, "b200_sscan_bwd: dout/du/ddelta/dA/dB/dC must be non-NULL");
     B200_REQUIRE((q->f.z == nullptr) == (q->dz == nullptr), "b200_sscan_bwd: dz must be given exactly when z is");
     B200_REQUIRE(q->dout_group_div >= 1, "b200_sscan_bwd: dout_group_div must be >= 1");
+    B200_REQUIRE(q->dB_state_stride >= q->f.seqlen && q->dC_state_stride >= q->f.seqlen &&
+                     (long long)q->f.dstate * q->dB_state_stride < (1ll << 31) && (long long)q->f.dstate * q->dC_state_stride < (1ll << 31),
+                 "b200_sscan_bwd: dB/dC state strides must be in [seqlen, 2^31 / dstate)");
     B200_REQUIRE(n_tasks(&q->f) < (1ll << 31), "b200_sscan_bwd: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
     switch (q->f.io_dtype) {

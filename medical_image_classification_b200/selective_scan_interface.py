@@ -45,8 +45,16 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+def _row_strides(t, rpg):
+    """(batch, group, row) element strides of an activation given as (B, dim, L) or as a (B, G', rows, L) view."""
+    if t.dim() == 4:
+        return t.stride(0), t.stride(1), t.stride(2)
+    return t.stride(0), rpg * t.stride(1), t.stride(1)
+
+
 def _fill_fwd(p, u, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, rev_mask, u_group_div):
-    batch, dim, L = delta.shape
+    """u, delta: (batch, dim, L), or 4-D views (batch, groups, rows per group, L) with arbitrary leading strides."""
+    batch, L, dim = delta.shape[0], delta.shape[-1], A.shape[0]
     G, N = Bm.shape[1], Bm.shape[2]
     rpg = dim // G
     p.batch, p.dim, p.seqlen, p.dstate, p.n_groups = batch, dim, L, N, G
@@ -54,9 +62,8 @@ def _fill_fwd(p, u, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, rev_mask
     p.delta_softplus = int(bool(delta_softplus))
     p.rev_mask = int(rev_mask)
     p.u_group_div = int(u_group_div)
-    p.u_batch_stride, p.u_row_stride = u.stride(0), u.stride(1)
-    p.u_group_stride = rpg * u.stride(1)
-    p.delta_batch_stride, p.delta_row_stride = delta.stride(0), delta.stride(1)
+    p.u_batch_stride, p.u_group_stride, p.u_row_stride = _row_strides(u, rpg)
+    p.delta_batch_stride, p.delta_group_stride, p.delta_row_stride = _row_strides(delta, rpg)
     p.B_batch_stride, p.B_group_stride, p.B_state_stride = Bm.stride(0), Bm.stride(1), Bm.stride(2)
     p.C_batch_stride, p.C_group_stride, p.C_state_stride = Cm.stride(0), Cm.stride(1), Cm.stride(2)
     if z is not None:
@@ -92,7 +99,7 @@ def launch_fwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, rev_mask=0
     """One b200_sscan_fwd call on prepared tensors (last stride 1, B/C 4-D, A/D/bias fp32 contiguous).
     Returns (out, last_state | None, ckpt | None)."""
     lib = _lib.load()
-    batch, dim, L = delta.shape
+    batch, L, dim = delta.shape[0], delta.shape[-1], A32.shape[0]
     G, N = Bm.shape[1], Bm.shape[2]
     out = torch.empty((batch, dim, L), dtype=u.dtype, device=u.device)
     ckpt = None
@@ -115,20 +122,25 @@ def launch_fwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, rev_mask=0
 
 
 def launch_bwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, ckpt, dout, rev_mask=0,
-               u_group_div=1, dout_group_div=1, has_D=True, has_bias=True):
+               u_group_div=1, dout_group_div=1, has_D=True, has_bias=True, ddelta=None, dB=None, dC=None):
     """One b200_sscan_bwd call.  `dout` is (batch, dim / dout_group_div, L).
-    Returns du (batch, dim, L), ddelta, dA, dB, dC (fp32), dD, ddelta_bias, dz."""
+    Returns du (batch, dim, L), ddelta, dA, dB, dC (fp32), dD, ddelta_bias, dz.
+    ddelta (batch, G, rows per group, L) and dB, dC (batch, G, N, L; fp32, ZERO-FILLED by the caller) may be passed as
+    views into a wider buffer (last stride 1); they are then written / accumulated in place."""
     lib = _lib.load()
-    batch, dim, L = delta.shape
+    batch, L, dim = delta.shape[0], delta.shape[-1], A32.shape[0]
     G, N = Bm.shape[1], Bm.shape[2]
     rpg = dim // G
     dev = u.device
     du = torch.empty((batch, dim, L), dtype=u.dtype, device=dev)
-    ddelta = torch.empty((batch, dim, L), dtype=u.dtype, device=dev)
+    if ddelta is None:
+        ddelta = torch.empty((batch, dim, L), dtype=u.dtype, device=dev)
     dz = torch.empty((batch, dim, L), dtype=u.dtype, device=dev) if z is not None else None
     # fp32 accumulators for everything reduced with atomics (selective_scan.cpp:460-466)
-    dB = torch.zeros((batch, G, N, L), dtype=torch.float32, device=dev)
-    dC = torch.zeros((batch, G, N, L), dtype=torch.float32, device=dev)
+    if dB is None:
+        dB = torch.zeros((batch, G, N, L), dtype=torch.float32, device=dev)
+    if dC is None:
+        dC = torch.zeros((batch, G, N, L), dtype=torch.float32, device=dev)
     dA = torch.zeros((dim, N), dtype=torch.float32, device=dev)
     dD = torch.zeros(dim, dtype=torch.float32, device=dev) if has_D else None
     dbias = torch.zeros(dim, dtype=torch.float32, device=dev) if has_bias else None
@@ -139,7 +151,9 @@ def launch_bwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, ckpt, dout
     q.dout_batch_stride, q.dout_row_stride = dout.stride(0), dout.stride(1)
     q.dout_group_stride, q.dout_group_div = rpg * dout.stride(1), int(dout_group_div)
     q.du_batch_stride, q.du_row_stride = du.stride(0), du.stride(1)
-    q.ddelta_batch_stride, q.ddelta_row_stride = ddelta.stride(0), ddelta.stride(1)
+    q.ddelta_batch_stride, q.ddelta_group_stride, q.ddelta_row_stride = _row_strides(ddelta, rpg)
+    q.dB_batch_stride, q.dB_group_stride, q.dB_state_stride = dB.stride(0), dB.stride(1), dB.stride(2)
+    q.dC_batch_stride, q.dC_group_stride, q.dC_state_stride = dC.stride(0), dC.stride(1), dC.stride(2)
     if dz is not None:
         q.dz_batch_stride, q.dz_row_stride = dz.stride(0), dz.stride(1)
     q.dout, q.du, q.ddelta, q.dz = dout.data_ptr(), du.data_ptr(), ddelta.data_ptr(), _lib.ptr(dz)

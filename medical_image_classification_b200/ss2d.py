@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .cross import cross_scan_pack, scan_merge
+from .cross import cross_scan_pack, scan_merge, ss2d_core  # noqa: F401
 from .selective_scan_interface import selective_scan_fn
 
 
@@ -264,14 +264,11 @@ class SS2D(nn.Module):
         R, N = self.dt_rank, self.d_state
         tf32 = torch.is_autocast_enabled()   # the reference computes these projections in bf16 under autocast
         with torch.autocast("cuda", enabled=False):
-            x2 = cross_scan_pack(x.float())                         # (B, 2, D, L)
             Wx, Wdt, bias, As, Ds = self._dir_params()
-            # directions (0,1) read x2[:,0], (2,3) read x2[:,1]: one GEMM per layout
-            x_dbl = _ProjFn.apply(Wx.reshape(2, 2 * (R + 2 * N), D).unsqueeze(0), x2, tf32)   # (B, 2, 2C, L)
-            x_dbl = x_dbl.view(B, 4, R + 2 * N, L)
-            dts_r, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-            dts = _ProjFn.apply(Wdt.unsqueeze(0), dts_r, tf32)       # (B, 4, D, L)
-            y = scan_merge(x2, dts.view(B, 4 * D, L), As, Bs, Cs, Ds, bias, H, W)      # (B, L, D)
+            # one projection matrix per direction: rows of B, rows of C, and the rank-R dt projection folded through
+            # x_proj's dt rows (delta = Wdt (Wx_dt x) = (Wdt Wx_dt) x), so B, C and delta come out of ONE GEMM
+            W_all = torch.cat([Wx[:, R:], torch.matmul(Wdt, Wx[:, :R])], dim=1)              # (4, 2N + D, D)
+            y = ss2d_core(x, W_all, As, Ds, bias, N, tf32)                                    # (B, L, D)
         return y.view(B, H, W, D)
 
     def forward_core_api(self, x: torch.Tensor):
