@@ -13,7 +13,7 @@ from functools import partial
 import torch
 import torch.nn as nn
 
-from .ss2d import SS2D
+from .ss2d import SS2D, split_halves
 from .ss2d_ssd import SS2D_with_SSD
 
 
@@ -121,20 +121,6 @@ class ShuffleCatAddFn(torch.autograd.Function):
         return dleft, dx, dout
 
 
-class SplitHalvesFn(torch.autograd.Function):
-    """left, right = input.chunk(2, dim=-1) (MedMamba.py:530) with a one-pass backward: d(input) = cat(d left, d right)
-    instead of two zero-filled full-size buffers, two slice copies and an add."""
-
-    @staticmethod
-    def forward(ctx, inp):
-        c = inp.shape[-1] // 2
-        return inp[..., :c], inp[..., c:]
-
-    @staticmethod
-    def backward(ctx, dl, dr):
-        return torch.cat((dl, dr.to(dl.dtype)), dim=-1)
-
-
 class SS_Conv_SSM(nn.Module):
     """Two-branch block: half the channels through conv3x3-conv3x3-conv1x1, half through
     LayerNorm -> SS2D; concat, channel shuffle, residual."""
@@ -159,7 +145,7 @@ class SS_Conv_SSM(nn.Module):
         )
 
     def forward(self, input):
-        left, right = SplitHalvesFn.apply(input) if (input.is_cuda and input.shape[-1] % 2 == 0) else input.chunk(2, dim=-1)
+        left, right = split_halves(input)
         if right.is_cuda and right.dtype in (torch.float32, torch.bfloat16) and isinstance(self.ln_1, nn.LayerNorm) and right.shape[-1] <= 1024:
             from .ss2d import layer_norm_rows
             normed = layer_norm_rows(right, self.ln_1)     # pre-norm, the right half read in place (csrc/lngate.cu)

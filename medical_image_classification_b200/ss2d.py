@@ -76,6 +76,28 @@ def _rows_view(t, D):
     return (t, t.stride(-2)) if ok else (t.contiguous(), D)
 
 
+class SplitHalvesFn(torch.autograd.Function):
+    """a, b = t.chunk(2, dim=-1) (MedMamba.py:467 `x, z = xz.chunk(2, dim=-1)`, :530 `left, right = input.chunk(...)`) with a
+    one-pass backward: d(input) = cat(d left, d right)
+    instead of two zero-filled full-size buffers, two slice copies and an add."""
+
+    @staticmethod
+    def forward(ctx, inp):
+        c = inp.shape[-1] // 2
+        return inp[..., :c], inp[..., c:]
+
+    @staticmethod
+    def backward(ctx, dl, dr):
+        return torch.cat((dl, dr.to(dl.dtype)), dim=-1)
+
+
+def split_halves(t):
+    """t.chunk(2, dim=-1); on CUDA with an even last dimension through SplitHalvesFn (one cat in the backward)."""
+    if t.is_cuda and t.shape[-1] % 2 == 0 and t.requires_grad:
+        return SplitHalvesFn.apply(t)
+    return t.chunk(2, dim=-1)
+
+
 class LnGateFn(torch.autograd.Function):
     """out = LayerNorm(y) [* silu(z)] in one pass over HBM (csrc/lngate.cu) -- reference MedMamba.py:478-479 (with z)
     and the block pre-norm `ln_1` (MedMamba.py:531, z = None).  y (..., D) fp32 (or bf16 when z is None: the bf16 residual
@@ -295,7 +317,7 @@ class SS2D(nn.Module):
     def forward(self, x: torch.Tensor, **kwargs):
         B, H, W, C = x.shape
         xz = self.in_proj(x)
-        x, z = xz.chunk(2, dim=-1)
+        x, z = split_halves(xz)
         if (x.is_cuda and self.d_conv == 3 and W <= 64 and x.dtype in (torch.float32, torch.bfloat16)
                 and self.forward_core == self.forward_core_fused):
             x = DwConvSiluFn.apply(x, self.conv2d.weight, self.conv2d.bias)   # conv3x3 + SiLU, channels-last in -> fp32 planes out

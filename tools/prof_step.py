@@ -28,3 +28,11 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+# kernel-only view: device-side events, per step
+from torch.autograd import DeviceType
+ks = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA]
+ks.sort(key=lambda e: -e.self_device_time_total)
+tot = sum(e.self_device_time_total for e in ks)
+print(f"\n== kernels: {tot / 3e3:.2f} ms of device time per step ==")
+for e in ks[:70]:
+    print(f"{e.self_device_time_total / 3e3:8.3f} ms/step {e.count / 3:7.1f} launches/step  {e.key[:150]}")
