@@ -161,3 +161,29 @@ def test_ssd_twin_cross_scan4_and_merge4_are_bit_exact(shape):
     got = y.grad.clone(); y.grad = None
     ref.backward(go)
     assert torch.equal(got, y.grad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 5, 7, 6), (1, 3, 56, 56), (3, 4, 14, 14), (1, 2, 70, 66), (2, 3, 64, 64)])
+def test_strided_pack_and_unpack4_match_tensor_ops(shape):
+    """The fused core's cross-scan pair (csrc/cross.cu, whole-plane and 32x32-tile variants) in the (2, D, B, L) layout:
+    pack is pure data movement (bit-exact); unpack4 is the adjoint, a 6-term sum per element."""
+    from medical_image_classification_b200 import _lib
+    lib = _lib.load()
+    B, D, H, W = shape
+    L = H * W
+    torch.manual_seed(H)
+    x = torch.randn(B, D, H, W, device="cuda")
+    x2 = torch.full((2, D, B, L), float("nan"), device="cuda")
+    strides = (L, D * B * L, B * L)
+    sp = _lib.stream_ptr(x.device)
+    _lib.check(lib.b200_cross_scan_pack_strided(x.data_ptr(), x2.data_ptr(), *strides, B, D, H, W, sp), "pack")
+    assert torch.equal(x2[0].permute(1, 0, 2), x.reshape(B, D, L))
+    assert torch.equal(x2[1].permute(1, 0, 2), x.transpose(2, 3).reshape(B, D, L))
+    du = torch.randn(B, 4, D, L, device="cuda")
+    g2 = torch.randn(2, D, B, L, device="cuda")
+    dx = torch.full((B, D, H, W), float("nan"), device="cuda")
+    _lib.check(lib.b200_cross_scan_unpack4(du.data_ptr(), g2.data_ptr(), *strides, dx.data_ptr(), B, D, H, W, sp), "unpack4")
+    hw = (du[:, 0] + du[:, 1] + g2[0].permute(1, 0, 2)).view(B, D, H, W)
+    wh = (du[:, 2] + du[:, 3] + g2[1].permute(1, 0, 2)).view(B, D, W, H).transpose(2, 3)
+    assert torch.allclose(dx, hw + wh, rtol=0, atol=4e-6)
