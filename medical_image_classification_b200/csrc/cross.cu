@@ -415,6 +415,152 @@ __global__ void __launch_bounds__(CS_THREADS) cross_scan_unpack4_plane_kernel(co
     }
 }
 
+
+// ---- 128-bit whole-plane variants (H, W multiples of 4, both <= 64; all MedMamba stages but the 7 x 7 one).
+// Phase 1 moves float4 along the source's contiguous axis (16 lanes per row) into an aligned shared tile; phase 2 builds the
+// float4 of the transposed side from 4 shared rows with lanes arranged 8 (contiguous axis of the tile) x 4 (float4 slots), so
+// that shared reads are at most 2-way conflicted and every group of 4 lanes touches 64 contiguous bytes of global memory.
+constexpr int CS_V_MAX = 64;
+constexpr int CS_V_PITCH = CS_V_MAX + 4;
+
+__global__ void __launch_bounds__(CS_THREADS) cross_scan_pack_v4_kernel(const float* __restrict__ x, float* __restrict__ x2, int64_t sB, int64_t sI,
+                                                                        int64_t sD, int D, int H, int W, int nplanes) {
+    __shared__ __align__(16) float S[CS_V_MAX * CS_V_PITCH];     // S[h][w]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lane = tid & 31, warp = tid >> 5, a_l = lane & 7, q_l = lane >> 3;
+    const int W4 = W >> 2, H4 = H >> 2, L = H * W;
+    for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+        const int b = plane / D, d = plane % D;
+        const float4* src = reinterpret_cast<const float4*>(x + (size_t)plane * L);
+        float* dst0 = x2 + (size_t)b * sB + (size_t)d * sD;
+        float* dst1 = dst0 + sI;
+        if (tx < W4) {
+#pragma unroll 4
+            for (int h = ty; h < H; h += 16) {
+                const float4 v = __ldcs(src + h * W4 + tx);
+                reinterpret_cast<float4*>(dst0)[h * W4 + tx] = v;
+                *reinterpret_cast<float4*>(&S[h * CS_V_PITCH + 4 * tx]) = v;
+            }
+        }
+        __syncthreads();
+        const int w = warp * 8 + a_l;                            // 8 warps x 8 columns cover W <= 64
+        if (w < W) {
+#pragma unroll 4
+            for (int h4 = q_l; h4 < H4; h4 += 4) {
+                const float* col = &S[(4 * h4) * CS_V_PITCH + w];
+                const float4 v = make_float4(col[0], col[CS_V_PITCH], col[2 * CS_V_PITCH], col[3 * CS_V_PITCH]);
+                reinterpret_cast<float4*>(dst1 + (size_t)w * H)[h4] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__global__ void __launch_bounds__(CS_THREADS) cross_scan_unpack4_v4_kernel(const float* __restrict__ du, const float* __restrict__ gx2, int64_t sB,
+                                                                           int64_t sI, int64_t sD, float* __restrict__ dx, int D, int H, int W,
+                                                                           int nplanes) {
+    __shared__ __align__(16) float S[CS_V_MAX * CS_V_PITCH];     // S[w][h]: the column-major directions, summed
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lane = tid & 31, warp = tid >> 5, a_l = lane & 7, q_l = lane >> 3;
+    const int W4 = W >> 2, H4 = H >> 2, L = H * W;
+    const size_t DL = (size_t)D * L;
+    for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+        const int b = plane / D, d = plane % D;
+        const float* u0 = du + ((size_t)b * 4 * D + d) * L;
+        const float* g0 = gx2 + (size_t)b * sB + (size_t)d * sD;
+        const float* g1 = g0 + sI;
+        if (tx < H4) {
+            const float4* a = reinterpret_cast<const float4*>(u0 + 2 * DL);
+            const float4* c = reinterpret_cast<const float4*>(u0 + 3 * DL);
+            const float4* e = reinterpret_cast<const float4*>(g1);
+#pragma unroll 4
+            for (int w = ty; w < W; w += 16) {
+                const int o = w * H4 + tx;
+                *reinterpret_cast<float4*>(&S[w * CS_V_PITCH + 4 * tx]) = add4(add4(__ldcs(a + o), __ldcs(c + o)), __ldcs(e + o));
+            }
+        }
+        __syncthreads();
+        const int h = warp * 8 + a_l;                            // 8 warps x 8 rows cover H <= 64
+        if (h < H) {
+            const float4* a = reinterpret_cast<const float4*>(u0) + h * W4;
+            const float4* c = reinterpret_cast<const float4*>(u0 + DL) + h * W4;
+            const float4* e = reinterpret_cast<const float4*>(g0) + h * W4;
+            float4* dst = reinterpret_cast<float4*>(dx + (size_t)plane * L) + h * W4;
+#pragma unroll 4
+            for (int w4 = q_l; w4 < W4; w4 += 4) {
+                const float* col = &S[(4 * w4) * CS_V_PITCH + h];
+                const float4 t = make_float4(col[0], col[CS_V_PITCH], col[2 * CS_V_PITCH], col[3 * CS_V_PITCH]);
+                __stcs(dst + w4, add4(add4(add4(__ldcs(a + w4), __ldcs(c + w4)), __ldcs(e + w4)), t));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+
+// ---- small planes (H * W <= CS_WARP_MAX, e.g. 14 x 14 and 7 x 7): one WARP per plane, eight planes in flight per CTA, private
+//      shared tile per warp, no block barrier.
+constexpr int CS_WARP_MAX = 1024;
+
+__global__ void __launch_bounds__(CS_THREADS) cross_scan_pack_warp_kernel(const float* __restrict__ x, float* __restrict__ x2, int64_t sB, int64_t sI,
+                                                                          int64_t sD, int D, int H, int W, int nplanes) {
+    extern __shared__ float plane_s[];
+    const int L = H * W, PW = W | 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* T = plane_s + warp * (H * PW);
+    for (int plane = blockIdx.x * (CS_THREADS / 32) + warp; plane < nplanes; plane += gridDim.x * (CS_THREADS / 32)) {
+        const int b = plane / D, d = plane % D;
+        const float* src = x + (size_t)plane * L;
+        float* dst0 = x2 + (size_t)b * sB + (size_t)d * sD;
+        float* dst1 = dst0 + sI;
+#pragma unroll 4
+        for (int p = lane; p < L; p += 32) {
+            const float v = __ldcs(src + p);
+            const int h = p / W, w = p - h * W;
+            dst0[p] = v;
+            T[h * PW + w] = v;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int o = lane; o < L; o += 32) {
+            const int w = o / H, h = o - w * H;
+            dst1[o] = T[h * PW + w];
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(CS_THREADS) cross_scan_unpack4_warp_kernel(const float* __restrict__ du, const float* __restrict__ gx2, int64_t sB,
+                                                                             int64_t sI, int64_t sD, float* __restrict__ dx, int D, int H, int W,
+                                                                             int nplanes) {
+    extern __shared__ float plane_s[];
+    const int L = H * W, PH = H | 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t DL = (size_t)D * L;
+    float* T = plane_s + warp * (W * PH);
+    for (int plane = blockIdx.x * (CS_THREADS / 32) + warp; plane < nplanes; plane += gridDim.x * (CS_THREADS / 32)) {
+        const int b = plane / D, d = plane % D;
+        const float* u0 = du + ((size_t)b * 4 * D + d) * L;
+        const float* g0 = gx2 + (size_t)b * sB + (size_t)d * sD;
+        const float* g1 = g0 + sI;
+        float* dst = dx + (size_t)plane * L;
+#pragma unroll 4
+        for (int o = lane; o < L; o += 32) {
+            const float v = __ldcs(u0 + 2 * DL + o) + __ldcs(u0 + 3 * DL + o) + __ldcs(g1 + o);
+            const int w = o / H, h = o - w * H;
+            T[w * PH + h] = v;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int p = lane; p < L; p += 32) {
+            const float v = __ldcs(u0 + p) + __ldcs(u0 + DL + p) + __ldcs(g0 + p);
+            const int h = p / W, w = p - h * W;
+            __stcs(dst + p, v + T[w * PH + h]);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -444,6 +590,24 @@ extern "C" int b200_cross_scan_pack_strided(const float* x, float* x2, int64_t x
                                             int32_t batch, int32_t D, int32_t H, int32_t W, b200_stream_t stream) {
     if (int rc = check_dims(x, x2, batch, D, H, W, B200_F32, "b200_cross_scan_pack_strided")) return rc;
     B200_REQUIRE(x2_row_stride >= (int64_t)H * W || x2_batch_stride >= (int64_t)H * W, "b200_cross_scan_pack_strided: overlapping rows");
+    const bool v4 = H <= CS_V_MAX && W <= CS_V_MAX && (H & 3) == 0 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(x2) & 15) == 0 && (x2_batch_stride & 3) == 0 && (x2_layout_stride & 3) == 0 && (x2_row_stride & 3) == 0;
+    if (v4) {
+        const int nplanes = batch * D;
+        const int grid1 = nplanes < 148 * 8 ? nplanes : 148 * 8;
+        cross_scan_pack_v4_kernel<<<grid1, CS_THREADS, 0, (cudaStream_t)stream>>>(x, x2, x2_batch_stride, x2_layout_stride, x2_row_stride, D, H, W,
+                                                                                 nplanes);
+        return check_launch("cross_scan_pack_v4_kernel");
+    }
+    if (H * W <= CS_WARP_MAX && (size_t)(CS_THREADS / 32) * H * (W | 1) * sizeof(float) <= 48 * 1024) {
+        const int nplanes = batch * D;
+        const size_t smem = (size_t)(CS_THREADS / 32) * H * (W | 1) * sizeof(float);
+        const int want = (nplanes + CS_THREADS / 32 - 1) / (CS_THREADS / 32);
+        const int grid1 = want < 148 * 8 ? want : 148 * 8;
+        cross_scan_pack_warp_kernel<<<grid1, CS_THREADS, smem, (cudaStream_t)stream>>>(x, x2, x2_batch_stride, x2_layout_stride, x2_row_stride, D, H,
+                                                                                      W, nplanes);
+        return check_launch("cross_scan_pack_warp_kernel");
+    }
     if (H * W <= CS_PLANE_MAX) {
         const int nplanes = batch * D;
         const size_t smem = (size_t)H * (W | 1) * sizeof(float);
@@ -460,6 +624,25 @@ extern "C" int b200_cross_scan_unpack4(const float* du, const float* gx2, int64_
                                        float* dx, int32_t batch, int32_t D, int32_t H, int32_t W, b200_stream_t stream) {
     if (int rc = check_dims(du, dx, batch, D, H, W, B200_F32, "b200_cross_scan_unpack4")) return rc;
     B200_REQUIRE(gx2 != nullptr, "b200_cross_scan_unpack4: gx2 is NULL");
+    const bool v4 = H <= CS_V_MAX && W <= CS_V_MAX && (H & 3) == 0 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(du) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(gx2) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (x2_batch_stride & 3) == 0 &&
+                    (x2_layout_stride & 3) == 0 && (x2_row_stride & 3) == 0;
+    if (v4) {
+        const int nplanes = batch * D;
+        const int grid1 = nplanes < 148 * 8 ? nplanes : 148 * 8;
+        cross_scan_unpack4_v4_kernel<<<grid1, CS_THREADS, 0, (cudaStream_t)stream>>>(du, gx2, x2_batch_stride, x2_layout_stride, x2_row_stride, dx, D,
+                                                                                    H, W, nplanes);
+        return check_launch("cross_scan_unpack4_v4_kernel");
+    }
+    if (H * W <= CS_WARP_MAX && (size_t)(CS_THREADS / 32) * W * (H | 1) * sizeof(float) <= 48 * 1024) {
+        const int nplanes = batch * D;
+        const size_t smem = (size_t)(CS_THREADS / 32) * W * (H | 1) * sizeof(float);
+        const int want = (nplanes + CS_THREADS / 32 - 1) / (CS_THREADS / 32);
+        const int grid1 = want < 148 * 8 ? want : 148 * 8;
+        cross_scan_unpack4_warp_kernel<<<grid1, CS_THREADS, smem, (cudaStream_t)stream>>>(du, gx2, x2_batch_stride, x2_layout_stride, x2_row_stride,
+                                                                                         dx, D, H, W, nplanes);
+        return check_launch("cross_scan_unpack4_warp_kernel");
+    }
     if (H * W <= CS_PLANE_MAX) {
         const int nplanes = batch * D;
         const size_t smem = (size_t)W * (H | 1) * sizeof(float);

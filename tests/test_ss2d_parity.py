@@ -164,7 +164,7 @@ def test_ssd_twin_cross_scan4_and_merge4_are_bit_exact(shape):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(2, 5, 7, 6), (1, 3, 56, 56), (3, 4, 14, 14), (1, 2, 70, 66), (2, 3, 64, 64)])
+@pytest.mark.parametrize("shape", [(2, 5, 7, 6), (1, 3, 56, 56), (3, 4, 14, 14), (1, 2, 70, 66), (2, 3, 64, 64), (2, 3, 28, 28), (1, 2, 8, 12), (2, 2, 60, 4), (2, 3, 2, 300), (1, 2, 40, 90)])
 def test_strided_pack_and_unpack4_match_tensor_ops(shape):
     """The fused core's cross-scan pair (csrc/cross.cu, whole-plane and 32x32-tile variants) in the (2, D, B, L) layout:
     pack is pure data movement (bit-exact); unpack4 is the adjoint, a 6-term sum per element."""
