@@ -36,14 +36,16 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const TY* __
     const int64_t warp = (int64_t)blockIdx.x * LG_WARPS + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * LG_WARPS;
     const float invD = 1.f / (float)D;   // w / b are re-read per row (L1-resident): the row itself needs the registers
     for (int64_t r = warp; r < rows; r += nwarps) {
-        float v[NPL];
+        float v[NPL], zv[HAS_Z ? NPL : 1];   // every global load of the row is issued before the first use (latency-bound otherwise)
         float s = 0.f;
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int c = lane + 32 * k;
             v[k] = c < D ? ldg_stream(y + r * y_row_stride + c) : 0.f;
-            s += v[k];
+            if constexpr (HAS_Z) zv[k] = c < D ? ldg_stream(z + r * z_row_stride + c) : 0.f;
         }
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) s += v[k];
         const float mu = warp_sum(s) * invD;
         float q = 0.f;
 #pragma unroll
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_fwd_kernel(const TY* __
             if (c < D) {
                 const float n = (v[k] - mu) * rs * __ldg(w + c) + __ldg(b + c);
                 if constexpr (HAS_Z) {
-                    const float zz = ldg_stream(z + r * z_row_stride + c);
+                    const float zz = zv[k];
                     stg_stream(out + r * D + c, n * zz * sigmoidf_(zz));
                 } else {
                     stg_stream(out + r * D + c, n);
@@ -91,21 +93,29 @@ __global__ void __launch_bounds__(LG_WARPS * 32) ln_gate_bwd_kernel(const TO* __
     const float invD = 1.f / (float)D;
     for (int64_t r = warp; r < rows; r += nwarps) {
         const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
-        float xh[NPL], g[NPL];   // xhat, dn * w
+        float xh[NPL], g[NPL];   // y -> xhat, dout -> dn * w
+        float zv[HAS_Z ? NPL : 1];
         float s1 = 0.f, s2 = 0.f;
+        // every global load of the row is issued before the first use (one dependent round trip per row instead of NPL)
 #pragma unroll
         for (int k = 0; k < NPL; ++k) {
             const int c = lane + 32 * k;
+            xh[k] = c < D ? ldg_stream(y + r * y_row_stride + c) : 0.f;
+            g[k] = c < D ? ldg_stream(dout + r * D + c) : 0.f;
+            if constexpr (HAS_Z) zv[k] = c < D ? ldg_stream(z + r * z_row_stride + c) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NPL; ++k) {
+            const int c = lane + 32 * k;
+            const float yy = xh[k], go = g[k];
             xh[k] = 0.f;
             g[k] = 0.f;
             if (c < D) {
-                const float yy = ldg_stream(y + r * y_row_stride + c);
-                const float go = ldg_stream(dout + r * D + c);
                 const float wc = __ldg(w + c);
                 xh[k] = (yy - mu) * rs;
                 float dn = go;
                 if constexpr (HAS_Z) {
-                    const float zz = ldg_stream(z + r * z_row_stride + c);
+                    const float zz = zv[k];
                     const float sg = sigmoidf_(zz);
                     const float n = xh[k] * wc + __ldg(b + c);
                     dn = go * zz * sg;
