@@ -139,6 +139,17 @@ int b200_cross_scan_unpack4(const float* du, const float* gx2, int64_t x2_batch_
                             float* dx, int32_t batch, int32_t D, int32_t H, int32_t W, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * EfficientVMamba atrous scan / merge, step 2 -- replaces EfficientScan / EfficientMerge of
+ * CrossMamba/FusionMamba/models/cross.py:139-190 / 34-92 (strided slices, transposes and four copies each way).
+ *   scan : x (B, C, H, W) -> xs (B, 4, C, H2*W2), H2 = ceil(H/2), W2 = ceil(W/2):
+ *          xs[b,k,c,idx] = x[b, c, 2i + (k&1), 2j + (k>>1)], idx = i*W2 + j for k even, j*H2 + i for k odd; zero beyond the image
+ *   merge: ys (B, 4, C, H2*W2) -> y (B, C, H, W), the inverse scatter.  Each is the other's adjoint (autograd uses that).
+ *   dtype in {F32, BF16, F16}; (H + 1) * (W + 2) <= 8192.
+ * ------------------------------------------------------------------------------------------ */
+int b200_atrous_scan(const void* x, void* xs, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t dtype, b200_stream_t stream);
+int b200_atrous_merge(const void* ys, void* y, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t dtype, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * SS2D cross-scan / cross-merge helpers (reference MedMamba.py:393-395, 420-424, 476-477).
  *
  * b200_cross_scan_pack:  x (batch, D, H, W)  ->  x2 (batch, 2, D, L):  x2[:,0] = x row-major,

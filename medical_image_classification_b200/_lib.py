@@ -80,7 +80,7 @@ EXPORTS = [
     "b200_cross_scan4", "b200_cross_scan4_bwd", "b200_ssd_merge4", "b200_ssd_merge4_bwd",
     "b200_ssd_workspace_bytes", "b200_ssd_bwd_scratch_bytes", "b200_ssd_fwd", "b200_ssd_bwd",
     "b200_rmsnorm_gated_fwd", "b200_rmsnorm_gated_bwd",
-    "b200_cross_scan_pack_strided", "b200_cross_scan_unpack4",
+    "b200_cross_scan_pack_strided", "b200_cross_scan_unpack4", "b200_atrous_scan", "b200_atrous_merge",
     "b200_ln_gate_grid", "b200_ln_gate_fwd", "b200_ln_gate_bwd",
     "b200_dwconv_silu_fwd", "b200_dwconv_silu_bwd",
     "b200_shuffle_cat_add_fwd", "b200_shuffle_cat_add_bwd",
@@ -131,6 +131,8 @@ def load() -> C.CDLL:
     lib.b200_dwconv_silu_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_shuffle_cat_add_fwd.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_shuffle_cat_add_bwd.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]
+    lib.b200_atrous_scan.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.b200_atrous_merge.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200_cross_scan_pack_strided.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]
     lib.b200_cross_scan_unpack4.argtypes = [vp, vp, i64, i64, i64, vp, i32, i32, i32, i32, vp]
     lib.b200_ln_gate_grid.argtypes = [i64]

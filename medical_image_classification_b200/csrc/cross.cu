@@ -561,6 +561,78 @@ __global__ void __launch_bounds__(CS_THREADS) cross_scan_unpack4_warp_kernel(con
     }
 }
 
+
+// ---- EfficientVMamba atrous scan / merge (reference CrossMamba/FusionMamba/models/cross.py:34-92, 139-190),
+//      step 2: the four "directions" are the four sub-lattices of the image, (row parity, column parity) = (k & 1, k >> 1), k even
+//      flattened row-major (i * W2 + j), k odd column-major (j * H2 + i), zero padded to even sizes.
+//      scan:  xs[b, k, c, idx] = x[b, c, 2 i + (k & 1), 2 j + (k >> 1)];   merge is the inverse scatter (and each is the other's adjoint).
+//      One CTA turns one plane through shared memory; both global sides are contiguous runs.
+constexpr int AT_PLANE_MAX = 8192;   // pixels of the full-resolution plane held in shared memory (32 KB)
+
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS) atrous_scan_kernel(const T* __restrict__ x, T* __restrict__ xs, int C, int H, int W, int nplanes) {
+    extern __shared__ float plane_s[];                 // [h][W | 1]
+    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, L2 = H2 * W2, L = H * W, PW = W | 1;
+    for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+        const int b = plane / C, c = plane % C;
+        const T* src = x + (size_t)plane * L;
+#pragma unroll 4
+        for (int p = threadIdx.x; p < L; p += CS_THREADS) {
+            const int h = p / W, w = p - h * W;
+            plane_s[h * PW + w] = to_f32<T>(src[p]);
+        }
+        __syncthreads();
+        for (int k = 0; k < 4; ++k) {
+            T* dst = xs + (((size_t)b * 4 + k) * C + c) * L2;
+            const int hr = k & 1, wr = k >> 1;
+#pragma unroll 4
+            for (int o = threadIdx.x; o < L2; o += CS_THREADS) {
+                int i, j;
+                if (hr == 0) { i = o / W2; j = o - i * W2; } else { j = o / H2; i = o - j * H2; }
+                const int h = 2 * i + hr, w = 2 * j + wr;
+                dst[o] = from_f32<T>((h < H && w < W) ? plane_s[h * PW + w] : 0.f);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS) atrous_merge_kernel(const T* __restrict__ ys, T* __restrict__ y, int C, int H, int W, int nplanes) {
+    extern __shared__ float plane_s[];                 // [4][L2]
+    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, L2 = H2 * W2, L = H * W;
+    for (int plane = blockIdx.x; plane < nplanes; plane += gridDim.x) {
+        const int b = plane / C, c = plane % C;
+        for (int k = 0; k < 4; ++k) {
+            const T* src = ys + (((size_t)b * 4 + k) * C + c) * L2;
+#pragma unroll 4
+            for (int o = threadIdx.x; o < L2; o += CS_THREADS) plane_s[k * L2 + o] = to_f32<T>(src[o]);
+        }
+        __syncthreads();
+        T* dst = y + (size_t)plane * L;
+#pragma unroll 4
+        for (int p = threadIdx.x; p < L; p += CS_THREADS) {
+            const int h = p / W, w = p - h * W;
+            const int hr = h & 1, wr = w & 1, i = h >> 1, j = w >> 1;
+            dst[p] = from_f32<T>(plane_s[(hr + 2 * wr) * L2 + (hr == 0 ? i * W2 + j : j * H2 + i)]);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+static int run_atrous(const void* src, void* dst, int batch, int C, int H, int W, bool merge, cudaStream_t st) {
+    const int nplanes = batch * C;
+    const int grid1 = nplanes < 148 * 8 ? nplanes : 148 * 8;
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    if (!merge) {
+        atrous_scan_kernel<T><<<grid1, CS_THREADS, (size_t)H * (W | 1) * sizeof(float), st>>>((const T*)src, (T*)dst, C, H, W, nplanes);
+        return check_launch("atrous_scan_kernel");
+    }
+    atrous_merge_kernel<T><<<grid1, CS_THREADS, (size_t)4 * H2 * W2 * sizeof(float), st>>>((const T*)src, (T*)dst, C, H, W, nplanes);
+    return check_launch("atrous_merge_kernel");
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -584,6 +656,17 @@ extern "C" int b200_cross_merge_bwd(const void* dy, void* dys, int32_t batch, in
                                     b200_stream_t stream) {
     if (int rc = check_dims(dy, dys, batch, D, H, W, dtype, "b200_cross_merge_bwd")) return rc;
     DISPATCH(run_merge, dy, dys, batch, D, H, W, true, (cudaStream_t)stream)
+}
+
+extern "C" int b200_atrous_scan(const void* x, void* xs, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t dtype, b200_stream_t stream) {
+    if (int rc = check_dims(x, xs, batch, C, H, W, dtype, "b200_atrous_scan")) return rc;
+    B200_REQUIRE((long long)(H + 1) * (W + 2) <= AT_PLANE_MAX, "b200_atrous_scan: plane %d x %d exceeds %d pixels", H, W, AT_PLANE_MAX);
+    DISPATCH(run_atrous, x, xs, batch, C, H, W, false, (cudaStream_t)stream)
+}
+extern "C" int b200_atrous_merge(const void* ys, void* y, int32_t batch, int32_t C, int32_t H, int32_t W, int32_t dtype, b200_stream_t stream) {
+    if (int rc = check_dims(ys, y, batch, C, H, W, dtype, "b200_atrous_merge")) return rc;
+    B200_REQUIRE((long long)(H + 1) * (W + 2) <= AT_PLANE_MAX, "b200_atrous_merge: plane %d x %d exceeds %d pixels", H, W, AT_PLANE_MAX);
+    DISPATCH(run_atrous, ys, y, batch, C, H, W, true, (cudaStream_t)stream)
 }
 
 extern "C" int b200_cross_scan_pack_strided(const float* x, float* x2, int64_t x2_batch_stride, int64_t x2_layout_stride, int64_t x2_row_stride,
