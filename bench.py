@@ -361,15 +361,32 @@ def run_cuda(args):
     # ---- timed region 2: end to end (pinned host input -> device, loss -> host) ----
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Input pipeline of the public API path: every step's batch is copied from pinned host memory on a copy stream into one of
+    # two device staging buffers (what a pin_memory DataLoader with prefetch does), so step i+1's host->device copy overlaps step
+    # i's compute; the step then takes its batch from the staging buffer and the loss is read back to the host every step.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_x = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    stage_y = [torch.empty_like(y_dev), torch.empty_like(y_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            stage_x[i % 2].copy_(x_host, non_blocking=True)
+            stage_y[i % 2].copy_(y_host, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
     f0.record()
     last = 0.0
-    for _ in range(args.steps):
+    copy_stream.wait_stream(torch.cuda.current_stream())
+    prefetch(0)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            prefetch(i + 1)          # the buffer's previous reader (step i-1) finished: its loss was read back
+        torch.cuda.current_stream().wait_event(ready[i % 2])
         if graph is None:
-            xb = x_host.to(dev, non_blocking=True)
-            yb = y_host.to(dev, non_blocking=True)
-            last = eager_step(xb, yb).item()
+            last = eager_step(stage_x[i % 2], stage_y[i % 2]).item()
         else:
-            last = run_step(x_host, y_host).item()
+            last = run_step(stage_x[i % 2], stage_y[i % 2]).item()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -415,6 +432,7 @@ def run_cuda(args):
                            "l2": "per-step activations (> 10 GB) exceed the 126 MB L2; no explicit flush"},
                 "e2e": {"value": round(total / (ms_e2e / 1e3), 2), "unit": UNIT,
                         "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
+                        "input_pipeline": "pinned host batch -> device staging buffer on a copy stream, one step ahead (double buffered)",
                         "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": round(last, 4)},
                 "gpu_launches": launches, "roofline": roof, "scan_fwd_bwd": allscan, "clocks": clocks}
         if cpu_base is not None:
