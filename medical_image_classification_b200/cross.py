@@ -220,7 +220,9 @@ class SS2DCoreFn(torch.autograd.Function):
         big4 = big.view(4, M, B, L).permute(2, 0, 1, 3)
         g_big = torch.empty_like(big)
         g4 = g_big.view(4, M, B, L).permute(2, 0, 1, 3)                # (B, 4, M, L) view, like big4
-        g_big.view(4, M, B * L)[:, :2 * N].zero_()                     # dB, dC are accumulated with atomics; ddelta is written
+        gflat = g_big.view(4, M * B * L)
+        for k in range(4):                                             # dB, dC are accumulated with atomics (ddelta is written):
+            gflat[k, :2 * N * B * L].zero_()                           # four contiguous fills instead of one strided one
         du, _, dA, _, _, dD, dbias, _ = launch_bwd(x2.permute(2, 0, 1, 3), big4[:, :, 2 * N:], A32, big4[:, :, :N], big4[:, :, N:2 * N],
                                                    D32, None, b32, True, ckpt, d2, REV_MASK, 2, 2, True, True,
                                                    ddelta=g4[:, :, 2 * N:], dB=g4[:, :, :N], dC=g4[:, :, N:2 * N])
