@@ -1,5 +1,6 @@
 // cross.cu -- SS2D cross-scan / cross-merge data movement (reference MedMamba.py:393-395,
-// 420-424, 476-477; SSD twin SSD/MedSSD.py:332-336, 376-391).
+// 420-424, 476-477; SSD twin SSD/MedSSD.py:332-336, 376-391; atrous twin
+// CrossMamba/FusionMamba/models/cross.py:34-92, 139-190).
 //
 // The reference materialises four permuted copies of every channel plane (transpose, stack, flip,
 // cat: ~18 plane-sized passes) and later un-permutes four outputs (~19 passes).  Here the two
@@ -8,6 +9,14 @@
 // cross-merge is ONE pass that reads the four direction outputs and writes their sum in the
 // (B, H, W, D) layout the following LayerNorm wants.  All kernels are pure HBM streams; tiles are
 // turned through shared memory so that both the reads and the writes are contiguous runs.
+//
+// Kernel families in this file:
+//   cross_scan_pack[_bwd], cross_merge[_bwd]      32 x 32 / 8 x 8-patch tiles, contiguous (B, 2, D, L) layout (standalone entry points)
+//   cross_scan_pack_{v4,warp,plane,strided}       the pack for the fused SS2D core: x2 in a caller-given strided layout; 128-bit
+//   cross_scan_unpack4_{v4,warp,plane,tile}       whole-plane, warp-per-plane (small planes), scalar whole-plane and tile variants;
+//                                                 unpack4 = the whole adjoint (4 direction gradients + the projection's gradient)
+//   cross_scan4 / ssd_merge4 (+ adjoints)         SSD twins with four materialised directions
+//   atrous_scan / atrous_merge                    EfficientVMamba's four sub-lattice "directions" (each the other's adjoint)
 #include "common.cuh"
 
 namespace b200 {

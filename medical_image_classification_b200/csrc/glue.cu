@@ -6,6 +6,7 @@
 //   out[b, p, 2 j + 1] = x[b, p, j]    + input[b, p, 2 j + 1]    (x: the SS2D branch, channels-last)
 // i.e. a 32 x 32 plane-to-channels-last transpose fused with an interleave and an add: every global access is a
 // full coalesced row (lanes along pixels for the planes, along channels for the channels-last tensors).
+// input / out are fp32 or -- with bf16 left / x, the residual stream of stages 1-3 under autocast -- bf16 (sum in fp32, one rounding).
 #include "common.cuh"
 
 namespace b200 {

@@ -3,6 +3,7 @@
 // Replaces the three element-wise passes the reference runs after the cross-merge (reference MedMamba.py:478-479:
 // `y = self.out_norm(y); y = y * F.silu(z)`, LayerNorm over the d_inner channels, eps 1e-5) and their four autograd
 // kernels (layer-norm input grad, the gamma/beta reduction, silu backward, mul backward).  SURVEY.md section 8(f) rank 1.
+// y may be bf16 when z is absent (block pre-norm / PatchMerging norm on a bf16 residual stream; dy returns in bf16).
 // HBM-bound streaming kernels: one warp per row, the row lives in registers (d_inner <= 1024), statistics by
 // warp shuffles, one read of y / z / dout and one write of each output per element; d(weight), d(bias) are
 // accumulated per lane over the rows of a warp, combined per CTA in shared memory and written as per-CTA partials.
