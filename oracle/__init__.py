@@ -187,3 +187,34 @@ def cross_merge_ref(ys, H, W):
     invwh = inv[:, 1].reshape(Bn, Dn, W, H).transpose(0, 1, 3, 2).reshape(Bn, Dn, L)
     y = ys[:, 0] + inv[:, 0] + wh + invwh
     return np.ascontiguousarray(y.transpose(0, 2, 1)).reshape(Bn, H, W, Dn)
+
+
+# --------------------------------------------------------------------------------------
+# EfficientVMamba atrous scan / merge index maps (numpy), step 2
+# --------------------------------------------------------------------------------------
+def atrous_scan_ref(x):
+    """x (B, C, H, W) -> xs (B, 4, C, ceil(H/2) * ceil(W/2)).  CrossMamba/FusionMamba/models/cross.py:143-169 (EfficientScan.forward):
+    sub-lattice k has row parity k & 1 and column parity k >> 1; k even is flattened row-major, k odd column-major; zero padding."""
+    x = np.asarray(x)
+    Bn, Cn, H, W = x.shape
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    xp = np.zeros((Bn, Cn, 2 * H2, 2 * W2), x.dtype)
+    xp[:, :, :H, :W] = x
+    out = np.empty((Bn, 4, Cn, H2 * W2), x.dtype)
+    for k in range(4):
+        sub = xp[:, :, (k & 1)::2, (k >> 1)::2]                       # (B, C, H2, W2)
+        out[:, k] = (sub if k % 2 == 0 else sub.transpose(0, 1, 3, 2)).reshape(Bn, Cn, -1)
+    return out
+
+
+def atrous_merge_ref(ys, H, W):
+    """ys (B, 4, C, ceil(H/2) * ceil(W/2)) -> y (B, C, H * W).  models/cross.py:33-56 (EfficientMerge.forward)."""
+    ys = np.asarray(ys)
+    Bn, K, Cn, L2 = ys.shape
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    y = np.zeros((Bn, Cn, 2 * H2, 2 * W2), ys.dtype)
+    for k in range(4):
+        sub = ys[:, k].reshape(Bn, Cn, H2, W2) if k % 2 == 0 else ys[:, k].reshape(Bn, Cn, W2, H2).transpose(0, 1, 3, 2)
+        y[:, :, (k & 1)::2, (k >> 1)::2] = sub
+    return np.ascontiguousarray(y[:, :, :H, :W]).reshape(Bn, Cn, H * W)
+

@@ -1,8 +1,10 @@
 """Atrous scan / merge (csrc/cross.cu) against the reference's own tensor-op formulation
 (CrossMamba/FusionMamba/models/cross.py:139-190 EfficientScan, :34-92 EfficientMerge), restated here with the same slices.
-Pure data movement: bit-exact, forward and backward, odd sizes included (zero padding)."""
+Pure data movement: bit-exact, forward and backward, odd sizes included (zero padding); in fp32 also against the numpy oracle
+(oracle.atrous_scan_ref / atrous_merge_ref, pinned on CPU against the reference's own classes in tests/test_oracle_atrous.py)."""
 import math
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -58,6 +60,10 @@ def test_atrous_scan_and_merge_bit_exact(shape, dtype):
     got = ys.grad.clone(); ys.grad = None
     want.backward(g)
     assert torch.equal(got, ys.grad)
+    if dtype == torch.float32:
+        import oracle
+        assert np.array_equal(xs.detach().cpu().numpy(), oracle.atrous_scan_ref(x.detach().cpu().numpy()))
+        assert np.array_equal(y.detach().cpu().numpy(), oracle.atrous_merge_ref(ys.detach().cpu().numpy(), H, W))
     # the two maps are inverse to each other on the image
     assert torch.equal(EfficientMerge.apply(EfficientScan.apply(x.detach(), 2), H, W, 2).view(B, C, H, W), x.detach())
 
