@@ -143,6 +143,7 @@ def test_ssd_twin_cross_scan4_and_merge4_are_bit_exact(shape):
     hwwh = torch.stack([x.reshape(B, -1, L), x.transpose(2, 3).reshape(B, -1, L)], dim=1)
     ref4 = torch.cat([hwwh, hwwh.flip(-1)], dim=1)
     assert torch.equal(x4, ref4)
+    assert np.array_equal(x4.detach().cpu().numpy(), oracle.cross_scan_ref(x.detach().cpu().numpy()))   # the pinned index oracle
     g4 = torch.randn_like(x4)
     x4.backward(g4)
     got = wide.grad.clone(); wide.grad = None
@@ -156,6 +157,8 @@ def test_ssd_twin_cross_scan4_and_merge4_are_bit_exact(shape):
     invwh_y = inv_y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
     ref = y[:, :, 0] + inv_y[:, :, 0] + wh_y + invwh_y
     assert torch.allclose(out, ref, rtol=0, atol=2e-6)
+    want = oracle.cross_merge_ref(y.detach().cpu().numpy().transpose(0, 2, 3, 1), H, W).reshape(B, L, d)   # ys[b, k, d, l] = y[b, l, k, d]
+    assert np.abs(out.detach().cpu().numpy() - want).max() < 4e-6
     go = torch.randn_like(out)
     out.backward(go)
     got = y.grad.clone(); y.grad = None
