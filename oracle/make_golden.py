@@ -216,10 +216,46 @@ def crossmamba_case(name, d_model, d_state, headdim, H, W, batch, seed=0):
     print("wrote crossmamba", name, float(o1.abs().max()), float(o2.abs().max()))
 
 
+def _fusionmamba_scan_merge():
+    """EfficientMerge / EfficientScan of CrossMamba/FusionMamba/models/cross.py (:34-90, :139-190).  The module cannot be imported
+    whole (mamba_ssm, timm and a compiled selective_scan_cuda at import time), so the two autograd classes -- pure tensor ops --
+    are compiled from their source lines in place, unmodified."""
+    import math
+    import torch.nn.functional as F
+    path = os.path.join(ref_import.REF_ROOT if hasattr(ref_import, "REF_ROOT") else "/root/reference", "CrossMamba/FusionMamba/models/cross.py")
+    lines = open(path).read().split("\n")
+    src = "\n".join(lines[33:90]) + "\n\n" + "\n".join(lines[138:190]) + "\n"
+    ns = {"torch": torch, "F": F, "math": math}
+    exec(compile(src, path, "exec"), ns)
+    return ns["EfficientScan"], ns["EfficientMerge"]
+
+
+def atrous_case(name, B, C, H, W, seed=0):
+    """x -> xs = EfficientScan(x); ys -> y = EfficientMerge(ys), plus their autograd gradients, from the reference classes."""
+    Scan, Merge = _fusionmamba_scan_merge()
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+    xs = Scan.apply(x, 2)
+    gxs = torch.randn(xs.shape, generator=g)
+    xs.backward(gxs)
+    ys = torch.randn(xs.shape, generator=g, requires_grad=True)
+    y = Merge.apply(ys, H, W, 2)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    np.savez_compressed(os.path.join(OUT, f"atrous_{name}.npz"), x=_np(x), xs=_np(xs), gxs=_np(gxs), dx=_np(x.grad), ys=_np(ys), y=_np(y),
+                        gy=_np(gy), dys=_np(ys.grad))
+    print("wrote atrous", name, tuple(xs.shape))
+
+
 def main():
     assert ref_import.available(), "/root/reference is not mounted"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--atrous-only" in sys.argv:
+        atrous_case("8x8", 2, 3, 8, 8)
+        atrous_case("7x9", 1, 5, 7, 9, seed=1)
+        atrous_case("14x14", 2, 2, 14, 14, seed=2)
+        return
     if "--crossmamba-only" in sys.argv:
         crossmamba_case("d32_6x5", 32, 8, 16, 6, 5, 2)
         return
@@ -246,6 +282,9 @@ def main():
     ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
     medssd_case()
     crossmamba_case("d32_6x5", 32, 8, 16, 6, 5, 2)
+    atrous_case("8x8", 2, 3, 8, 8)
+    atrous_case("7x9", 1, 5, 7, 9, seed=1)
+    atrous_case("14x14", 2, 2, 14, 14, seed=2)
 
 
 if __name__ == "__main__":

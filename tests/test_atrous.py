@@ -98,3 +98,28 @@ def test_cross_selective_scan_new_matches_tensor_op_formulation():
     ref = torch.autograd.grad(want, params, g)
     for a, b_ in zip(got, ref):
         assert float((a - b_).abs().max() / b_.abs().max().clamp_min(1e-30)) < 1e-5
+
+
+import glob  # noqa: E402
+import os  # noqa: E402
+
+ATROUS_GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "atrous_*.npz")))
+
+
+@pytest.mark.parametrize("path", ATROUS_GOLDEN, ids=[os.path.basename(p)[7:-4] for p in ATROUS_GOLDEN])
+def test_atrous_kernels_match_reference_vectors(path):
+    """Vectors produced by the reference's own EfficientScan / EfficientMerge classes (oracle/make_golden.py --atrous-only)."""
+    from medical_image_classification_b200.atrous import EfficientMerge, EfficientScan
+    g = np.load(path)
+    B, C, H, W = g["x"].shape
+    x = torch.tensor(g["x"]).cuda().requires_grad_()
+    xs = EfficientScan.apply(x, 2)
+    assert np.array_equal(xs.detach().cpu().numpy(), g["xs"])
+    xs.backward(torch.tensor(g["gxs"]).cuda())
+    assert np.array_equal(x.grad.cpu().numpy(), g["dx"])
+    ys = torch.tensor(g["ys"]).cuda().requires_grad_()
+    y = EfficientMerge.apply(ys, H, W, 2)
+    assert np.array_equal(y.detach().cpu().numpy(), g["y"])
+    y.backward(torch.tensor(g["gy"]).cuda())
+    assert np.array_equal(ys.grad.cpu().numpy(), g["dys"])
+

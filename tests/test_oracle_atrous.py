@@ -50,3 +50,20 @@ def test_atrous_oracle_matches_reference(shape):
         Scan, Merge = _reference_classes()
         assert np.array_equal(xs, Scan.apply(torch.tensor(x), 2).numpy())
         assert np.array_equal(y, Merge.apply(torch.tensor(ys), H, W, 2).numpy())
+
+
+GOLDENS = sorted(f for f in os.listdir(os.path.join(os.path.dirname(__file__), "golden")) if f.startswith("atrous_"))
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_atrous_oracle_matches_committed_reference_vectors(name):
+    """tests/golden/atrous_*.npz were produced by the reference's own EfficientScan / EfficientMerge (oracle/make_golden.py
+    --atrous-only); they travel to the GPU box, where /root/reference does not exist."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+    B, C, H, W = g["x"].shape
+    assert np.array_equal(oracle.atrous_scan_ref(g["x"]), g["xs"])
+    assert np.array_equal(oracle.atrous_merge_ref(g["ys"], H, W), g["y"])
+    # the reference's autograd: each map is the other's adjoint
+    assert np.array_equal(oracle.atrous_merge_ref(g["gxs"], H, W).reshape(B, C, H, W), g["dx"])
+    assert np.array_equal(oracle.atrous_scan_ref(g["gy"].reshape(B, C, H, W)), g["dys"])
+
