@@ -1078,6 +1078,13 @@ static int launch_bwd(const b200_sscan_bwd_params* q, cudaStream_t st) {
 
 }  // namespace b200
 
+namespace b200 {
+namespace v2 {   // sscan2.cu: TMA-staged kernels for fp32 tensors with 16-byte aligned layouts
+bool try_fwd(const b200_sscan_fwd_params* p, cudaStream_t st, int* rc);
+bool try_bwd(const b200_sscan_bwd_params* q, cudaStream_t st, int* rc);
+}
+}
+
 using namespace b200;
 
 extern "C" size_t b200_sscan_ckpt_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t n_groups,
@@ -1096,6 +1103,10 @@ extern "C" int b200_sscan_fwd(const b200_sscan_fwd_params* p, b200_stream_t stre
     B200_REQUIRE(p->out != nullptr, "b200_sscan_fwd: out is NULL");
     B200_REQUIRE(n_tasks(p) < (1ll << 31), "b200_sscan_fwd: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        int rc = 0;
+        if (v2::try_fwd(p, st, &rc)) return rc;
+    }
     switch (p->io_dtype) {
         case B200_F32: return launch_fwd<float>(p, st);
         case B200_BF16: return launch_fwd<__nv_bfloat16>(p, st);
@@ -1115,6 +1126,10 @@ extern "C" int b200_sscan_bwd(const b200_sscan_bwd_params* q, b200_stream_t stre
                  "b200_sscan_bwd: dB/dC state strides must be in [seqlen, 2^31 / dstate)");
     B200_REQUIRE(n_tasks(&q->f) < (1ll << 31), "b200_sscan_bwd: too many rows");
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        int rc = 0;
+        if (v2::try_bwd(q, st, &rc)) return rc;
+    }
     switch (q->f.io_dtype) {
         case B200_F32: return launch_bwd<float>(q, st);
         case B200_BF16: return launch_bwd<__nv_bfloat16>(q, st);

@@ -1,0 +1,89 @@
+// tma.cuh -- mbarrier / TMA (cp.async.bulk.tensor) device helpers and the host-side tensor-map encoder, sm_100a.
+// The encoder is fetched through cudaGetDriverEntryPoint, so the library does not link libcuda.
+#pragma once
+#include <cuda.h>   // CUtensorMap (types only)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global -> shared tile load, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// shared -> global tile store / reduce-add (bulk async group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// generic-proxy accesses of a tile must be ordered before the async proxy (TMA) touches it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- host: cuTensorMapEncodeTiled ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tma_encoder() {
+    static const EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        (void)cudaGetLastError();
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+
+// fp32 tensor viewed as (L, rows, groups, batch) with element strides (1, row, group, batch); box = (box_l, box_rows, 1, 1).
+// All strides must be positive multiples of 4 elements (16 bytes), the base 16-byte aligned.
+inline bool tma_make_map_f32(CUtensorMap* m, const void* base, int L, int rows, int groups, int batch, int64_t row_stride,
+                             int64_t group_stride, int64_t batch_stride, int box_l, int box_rows, CUtensorMapSwizzle swz) {
+    const EncodeTiledFn enc = tma_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (row_stride & 3) || (group_stride & 3) || (batch_stride & 3)) return false;
+    if (row_stride <= 0 || group_stride <= 0 || batch_stride <= 0 || L <= 0 || rows <= 0 || groups <= 0 || batch <= 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)L, (cuuint64_t)rows, (cuuint64_t)groups, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)row_stride * 4, (cuuint64_t)group_stride * 4, (cuuint64_t)batch_stride * 4};
+    for (int k = 0; k < 3; ++k)
+        if (strides[k] >= (1ull << 40)) return false;
+    const cuuint32_t box[4] = {(cuuint32_t)box_l, (cuuint32_t)box_rows, 1, 1}, estr[4] = {1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace b200

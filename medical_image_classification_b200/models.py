@@ -259,7 +259,7 @@ def medmamba_t(num_classes=6, **kw):
     return VSSM(num_classes=num_classes, depths=[2, 2, 4, 2], dims=[96, 192, 384, 768], **kw)
 
 
-def medssd(num_classes=6, dims=(128, 256, 512, 1024), d_state=128, **kw):
+def medssd(num_classes=6, dims=(128, 256, 512, 1024), d_state=128, depths=(2, 2, 4, 2), **kw):
     """MedSSD: the SSD/MedSSD.py VSSM defaults (depths 2-2-4-2, dims 128-1024, d_state 128), BASELINE.json configs[2].
     MedSSD_kan / CNN_Mamba backbones are the same graph with d_state=16."""
-    return VSSM(num_classes=num_classes, depths=[2, 2, 4, 2], dims=list(dims), d_state=d_state, block=SS_Conv_SSD, **kw)
+    return VSSM(num_classes=num_classes, depths=list(depths), dims=list(dims), d_state=d_state, block=SS_Conv_SSD, **kw)
