@@ -102,9 +102,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
-        _build.build()
+    from . import build as _build
+    if _build.can_build():
+        _build.build()          # no-op when the digest stamp matches; rebuilds a stale .so after csrc edits (under a file lock)
+    elif not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing and nvcc is not available to build it: there is no fallback path")
     lib = C.CDLL(LIB_PATH)
     lib.b200_last_error.restype = C.c_char_p
     lib.b200_sscan_ckpt_bytes.restype = C.c_size_t
@@ -164,6 +166,19 @@ def require_cuda(*tensors) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("libb200ssm ops run on CUDA tensors only: there is no CPU fallback")
+
+
+def no_autocast(fn):
+    """Decorator for the forward / backward of every ctypes-backed autograd.Function: the kernels read raw data_ptr()s with a fixed
+    dtype, so nothing inside may be re-cast by an enclosing torch.autocast region (loss.backward() called inside the autocast
+    block runs the backward under autocast too; a torch.bmm in there would then hand a bf16 buffer to an fp32 kernel)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with torch.autocast("cuda", enabled=False):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 def launches() -> int:

@@ -14,6 +14,8 @@ import math
 
 import torch
 
+
+from ._lib import no_autocast as _no_autocast
 from . import _lib
 from .selective_scan_interface import selective_scan_fn
 
@@ -33,6 +35,7 @@ class EfficientScan(torch.autograd.Function):
     """x (B, C, H, W) -> xs (B, 4, C, ceil(H/2) * ceil(W/2)) -- reference models/cross.py:139-190."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, x, step_size=2):
         _check_step(step_size)
         _lib.require_cuda(x)
@@ -45,6 +48,7 @@ class EfficientScan(torch.autograd.Function):
         return xs
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, grad_xs):
         B, C, H, W = ctx.shape
         grad_xs = grad_xs.contiguous()
@@ -57,6 +61,7 @@ class EfficientMerge(torch.autograd.Function):
     """ys (B, 4, C, ceil(H/2) * ceil(W/2)) -> y (B, C, H * W) -- reference models/cross.py:34-92."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, ys, ori_h, ori_w, step_size=2):
         _check_step(step_size)
         _lib.require_cuda(ys)
@@ -71,6 +76,7 @@ class EfficientMerge(torch.autograd.Function):
         return y.view(B, C, H * W)
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, grad_y):
         B, C, H, W = ctx.shape
         grad_y = grad_y.contiguous()

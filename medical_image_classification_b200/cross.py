@@ -15,6 +15,8 @@ from __future__ import annotations
 
 import torch
 
+
+from ._lib import no_autocast as _no_autocast
 from . import _lib
 from .selective_scan_interface import _f32c, launch_bwd, launch_fwd
 
@@ -34,6 +36,7 @@ class CrossScanPackFn(torch.autograd.Function):
     """x (B, D, H, W) -> x2 (B, 2, D, L): x2[:,0] row-major image, x2[:,1] column-major image."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, x):
         _lib.require_cuda(x)
         x = x.contiguous()
@@ -44,6 +47,7 @@ class CrossScanPackFn(torch.autograd.Function):
         return x2
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dx2):
         H, W = ctx.hw
         dx2 = dx2.contiguous()
@@ -57,6 +61,7 @@ class CrossMergeFn(torch.autograd.Function):
     """ys (B, 4, D, L) at memory positions (internal direction order) -> y (B, L, D)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, ys, H, W):
         _lib.require_cuda(ys)
         ys = ys.contiguous()
@@ -68,6 +73,7 @@ class CrossMergeFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dy):
         H, W = ctx.hw
         dy = dy.contiguous()
@@ -87,6 +93,7 @@ class ScanMergeFn(torch.autograd.Function):
     """
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, x2, delta, A, Bs, Cs, Ds, delta_bias, H, W):
         _lib.require_cuda(x2, delta, A, Bs, Cs, Ds, delta_bias)
         B, two, D, L = x2.shape
@@ -110,6 +117,7 @@ class ScanMergeFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dy):
         u, delta, A32, Bs, Cs, D32, b32, ckpt = ctx.saved_tensors
         H, W = ctx.hw
@@ -177,6 +185,7 @@ class SS2DCoreFn(torch.autograd.Function):
     tf32: run the three GEMMs in TF32 (used under autocast, where the reference runs these einsums in bf16)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, x, W_all, A, Ds, delta_bias, N, tf32):
         _lib.require_cuda(x, W_all, A, Ds, delta_bias)
         lib = _lib.load()
@@ -208,6 +217,7 @@ class SS2DCoreFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dy):
         x2, big, Wm, A32, D32, b32, ckpt = ctx.saved_tensors
         B, D, H, W, M, N, tf32 = ctx.meta
@@ -247,6 +257,7 @@ class CrossScan4Fn(torch.autograd.Function):
     x4 (B, 4, C, L) in the reference's direction order (hw, wh, hw reversed, wh reversed; SSD/MedSSD.py:332-336)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, x):
         _lib.require_cuda(x)
         lib = _lib.load()
@@ -261,6 +272,7 @@ class CrossScan4Fn(torch.autograd.Function):
         return x4
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dx4):
         lib = _lib.load()
         H, W = ctx.hw
@@ -278,6 +290,7 @@ class SsdMerge4Fn(torch.autograd.Function):
     (SSD/MedSSD.py:380-391)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, y, H, W):
         _lib.require_cuda(y)
         lib = _lib.load()
@@ -291,6 +304,7 @@ class SsdMerge4Fn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dout):
         lib = _lib.load()
         B, L, d, H, W = ctx.meta

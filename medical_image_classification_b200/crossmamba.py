@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .cross import cross_scan4, ssd_merge4
 from .ssd_combined import RMSNormGated, mamba_chunk_scan_combined
 
 
@@ -74,15 +75,9 @@ class CrossMamba(nn.Module):
     def _scan_inputs(self, xs, bcdts, B, L):
         """Four-direction cross-scan of [x | B | C | dt] (reference :280-299) as (b, l, ...) views with L stride 1."""
         gn = self.ngroups * self.d_state
-        if xs.is_cuda:   # one pass per component (csrc/cross.cu::cross_scan4_kernel), channel slices read in place
-            from .cross import cross_scan4
-            x = cross_scan4(xs)
-            Bm, Cm, dt = (cross_scan4(t) for t in torch.split(bcdts, [gn, gn, self.nheads], dim=1))
-        else:
-            xb = torch.cat([xs, bcdts], dim=1)                                                # (B, c, H, W)
-            hwwh = torch.stack([xb.reshape(B, -1, L), xb.transpose(2, 3).reshape(B, -1, L)], dim=1)
-            x4 = torch.cat([hwwh, hwwh.flip(-1)], dim=1)                                      # (B, 4, c, L)
-            x, Bm, Cm, dt = torch.split(x4, [self.d_ssm, gn, gn, self.nheads], dim=2)
+        # one pass per component (csrc/cross.cu::cross_scan4_kernel), channel slices read in place; CPU tensors raise
+        x = cross_scan4(xs)
+        Bm, Cm, dt = (cross_scan4(t) for t in torch.split(bcdts, [gn, gn, self.nheads], dim=1))
         x = x.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (-1, self.headdim))     # (B, L, 4*nheads, P)
         Bm = Bm.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (self.ngroups, -1))   # (B, L, G, 4*N)
         Cm = Cm.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (self.ngroups, -1))
@@ -107,14 +102,7 @@ class CrossMamba(nn.Module):
                                           cu_seqlens=cu_seqlens, **kw)                         # (B, L, 4*nheads, P)
             y = y.reshape(B, L, K, -1)
             assert y.dtype == torch.float32
-            if y.is_cuda:                                                                      # cross-merge (:344-356)
-                from .cross import ssd_merge4
-                out = ssd_merge4(y, H, W).view(B, H, W, -1)
-            else:
-                inv_y = y[:, :, 2:4].flip(1)
-                wh_y = y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
-                invwh_y = inv_y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
-                out = (y[:, :, 0] + inv_y[:, :, 0] + wh_y + invwh_y).view(B, H, W, -1)
+            out = ssd_merge4(y, H, W).view(B, H, W, -1)                                        # cross-merge (:344-356), one gather pass
             if self.rmsnorm:
                 out = self.norm(out, z)
             if d_mlp > 0:

@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -27,6 +28,26 @@ int check_launch(const char* what) {
         return (int)e;
     }
     return 0;
+}
+
+cudaError_t func_attr_per_device(const void* kernel, cudaFuncAttribute attr, int value) {
+    struct Entry { const void* k; int attr; unsigned long long devs; };
+    static Entry table[512];
+    static int n = 0;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const unsigned long long bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* e = nullptr;
+    for (int i = 0; i < n; ++i)
+        if (table[i].k == kernel && table[i].attr == (int)attr) { e = &table[i]; break; }
+    if (e && (e->devs & bit)) return cudaSuccess;
+    const cudaError_t rc = cudaFuncSetAttribute(kernel, attr, value);
+    if (rc != cudaSuccess) return rc;
+    if (!e && n < 512) { table[n] = Entry{kernel, (int)attr, 0ull}; e = &table[n++]; }
+    if (e) e->devs |= bit;      // table full: the attribute is simply set again next time (cheap, never wrong)
+    return cudaSuccess;
 }
 
 }  // namespace b200

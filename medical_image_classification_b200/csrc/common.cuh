@@ -16,6 +16,11 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch(int n = 1);
 
+// cudaFuncSetAttribute acts on the CURRENT device's copy of a kernel: remember (kernel, device) pairs, not just "done once",
+// so a process that uses several GPUs (a model moved to cuda:1 after a run on cuda:0) opts in on each of them.
+// Returns cudaSuccess when the attribute is (already) set.  Host only; defined in api.cu.
+cudaError_t func_attr_per_device(const void* kernel, cudaFuncAttribute attr, int value);
+
 #define B200_REQUIRE(cond, ...)          \
     do {                                 \
         if (!(cond)) {                   \
@@ -68,29 +73,35 @@ __device__ __forceinline__ float lg2_approx(float x) {
     return y;
 }
 
-// softplus(x) (threshold 20) and sigmoid(x) = d softplus/dx from ONE exponential, ~25 instructions
-// (the libm route log1pf(expf(x)) costs ~80).  e = exp(x) with a Cody-Waite split of log2(e) so the
-// error does not grow with |x|; log1p(e) = 2 atanh(e / (2 + e)) (4-term series, |s| <= 1/9) for
-// e < 0.25, log2(1 + e) * ln2 otherwise (lg2.approx is only inaccurate next to 1).  Max relative
-// error ~5e-7 for both outputs (checked against float64 in tests/test_math_host.py).
+// softplus(x) (threshold 20, F.softplus / selective_scan_fwd_kernel.cuh:153-156) and sigmoid(x) = d softplus/dx from TWO
+// MUFU operations (the libm route log1pf(expf(x)) costs ~80 instructions; the first version of this function used four MUFUs:
+// ex2, lg2 and two rcp).  With e = exp(-|x|) in (0, 1]:
+//     softplus(x) = max(x, 0) + log1p(e),   log1p(e) = 2 atanh(s),  s = e / (2 + e) <= 1/3  (8-term odd series, remainder < 2e-9),
+//     sigmoid(x)  = x >= 0 ? 1 / (1 + e) : e / (1 + e),
+// and both quotients come from ONE reciprocal r = 1 / ((1 + e)(2 + e)).  e = ex2(-|x| log2 e) without a Cody-Waite split: its
+// relative error |x| 2^-24 is multiplied by e / (1 + e) in softplus, i.e. at most 1.2e-8 absolute.  Relative error of both outputs
+// < 6.5e-7 for x >= -6 and < |x| 1e-7 below (where they are < 3e-3); tests/test_math_host.py restates this routine in numpy float32
+// and checks it against float64.
 struct SoftplusSig { float sp, sig; };
 __device__ __forceinline__ SoftplusSig softplus_sigmoid(float x) {
-    const float xc = fminf(fmaxf(x, -86.f), 21.f);  // keeps 2^n a normal number; exp(-86) ~ 4e-38 is already 0 in effect
-    const float n = rintf(xc * 1.4426950408889634f);
-    float f = fmaf(xc, 1.4426950216293335f, -n);     // log2(e) = hi + lo
-    f = fmaf(xc, 1.9259629911266175e-8f, f);
-    const float e = ex2(f) * __int_as_float(((int)n + 127) << 23);
-    const float t = 1.f + e;
-    const float sig = e * rcp_approx(t);
-    const float s = e * rcp_approx(2.f + e);
+    const float e = ex2(-fabsf(x) * kLog2e);
+    const float t1 = 1.f + e, t2 = 2.f + e;
+    const float r = rcp_approx(t1 * t2);
+    const float inv1 = r * t2;                 // 1 / (1 + e)
+    const float s = e * (r * t1);              // e / (2 + e)
     const float s2 = s * s;
-    const float small = 2.f * s * fmaf(s2, fmaf(s2, fmaf(s2, 1.f / 7.f, 0.2f), 1.f / 3.f), 1.f);
-    const float big = lg2_approx(t) * 0.6931471805599453f;
-    SoftplusSig r;
-    r.sp = e < 0.25f ? small : big;
-    r.sig = sig;
-    if (x > 20.f) { r.sp = x; r.sig = 1.f; }
-    return r;
+    float p = fmaf(s2, 1.f / 15.f, 1.f / 13.f);
+    p = fmaf(s2, p, 1.f / 11.f);
+    p = fmaf(s2, p, 1.f / 9.f);
+    p = fmaf(s2, p, 1.f / 7.f);
+    p = fmaf(s2, p, 0.2f);
+    p = fmaf(s2, p, 1.f / 3.f);
+    p = fmaf(s2, p, 1.f);
+    SoftplusSig o;
+    o.sp = fmaf(s + s, p, fmaxf(x, 0.f));
+    o.sig = x >= 0.f ? inv1 : e * inv1;
+    if (x > 20.f) { o.sp = x; o.sig = 1.f; }
+    return o;
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }

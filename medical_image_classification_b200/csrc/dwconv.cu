@@ -316,7 +316,7 @@ static size_t dw_bwd_smem(int W) {
     return (in_words + (size_t)DW_C * dw_gp(W)) * sizeof(float);
 }
 template <class K> static int dw_set_smem(K kernel, size_t bytes) {
-    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    const cudaError_t e = func_attr_per_device((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return (int)e;
@@ -327,7 +327,7 @@ template <class K> static int dw_set_smem(K kernel, size_t bytes) {
 template <typename TI>
 static int dw_fwd(const void* xin, int64_t ps, const float* w, const float* b, float* out, int B, int D, int H, int W, cudaStream_t st) {
     const size_t smem = dw_fwd_smem(DW_MAXW);
-    static const int rc0 = dw_set_smem(dwconv_silu_fwd_kernel<TI>, smem);
+    const int rc0 = dw_set_smem(dwconv_silu_fwd_kernel<TI>, smem);   // per (kernel, device), see common.cuh
     if (rc0) return rc0;
     const long long grid = (long long)B * ((D + DW_C - 1) / DW_C) * ((H + DW_TF - 1) / DW_TF);
     dwconv_silu_fwd_kernel<TI><<<(unsigned)grid, DW_THREADS, dw_fwd_smem(W), st>>>((const TI*)xin, ps, w, b, out, B, D, H, W);
@@ -337,7 +337,7 @@ template <typename TI>
 static int dw_bwd(const float* g, const void* xin, int64_t ps, const float* w, const float* b, void* dxin, float* dw, float* db, int B, int D,
                   int H, int W, cudaStream_t st) {
     const size_t smem = dw_bwd_smem(DW_MAXW);
-    static const int rc0 = dw_set_smem(dwconv_silu_bwd_kernel<TI>, smem);
+    const int rc0 = dw_set_smem(dwconv_silu_bwd_kernel<TI>, smem);
     if (rc0) return rc0;
     const long long grid = (long long)B * ((D + DW_C - 1) / DW_C) * ((H + DW_TB - 1) / DW_TB);
     dwconv_silu_bwd_kernel<TI><<<(unsigned)grid, DW_THREADS, dw_bwd_smem(W), st>>>(g, (const TI*)xin, ps, w, b, (TI*)dxin, dw, db, B, D, H, W);

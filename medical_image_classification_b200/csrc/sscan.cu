@@ -966,7 +966,8 @@ static int validate(const b200_sscan_fwd_params* p) {
                  p->n_groups);
     B200_REQUIRE(p->io_dtype >= B200_F32 && p->io_dtype <= B200_F16, "b200_sscan: bad io_dtype %d", p->io_dtype);
     B200_REQUIRE(p->rev_mask == 0 || p->n_groups <= 32, "b200_sscan: rev_mask needs n_groups <= 32");
-    B200_REQUIRE(p->u_group_div >= 1, "b200_sscan: u_group_div must be >= 1");
+    B200_REQUIRE(p->u_group_div >= 1 && p->n_groups % p->u_group_div == 0, "b200_sscan: u_group_div %d must be >= 1 and divide n_groups %d",
+                 p->u_group_div, p->n_groups);
     B200_REQUIRE((long long)p->dstate * p->seqlen < (1ll << 31), "b200_sscan: dstate * seqlen must be < 2^31");
     B200_REQUIRE(p->u && p->delta && p->A && p->B && p->C, "b200_sscan: u/delta/A/B/C must be non-NULL");
     B200_REQUIRE(p->ckpt == nullptr || p->ckpt_every == TC, "b200_sscan: ckpt_every must be %d", TC);
@@ -981,7 +982,7 @@ static long long n_tasks(const b200_sscan_fwd_params* p) {
 
 // static shared memory only, but 12-16 resident warp-CTAs need the large carve-out
 template <typename K> static void prefer_smem(K kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    (void)func_attr_per_device((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 // ---- tensor maps for the TMA row path ---------------------------------------------------------------------------
@@ -1053,9 +1054,10 @@ static int launch_fwd(const b200_sscan_fwd_params* p, cudaStream_t st) {
 
 template <typename T>
 static int launch_bwd(const b200_sscan_bwd_params* q, cudaStream_t st) {
-    static const bool once = (prefer_smem(sscan_bwd_kernel<T, true, false>), prefer_smem(sscan_bwd_kernel<T, false, false>),
-                              prefer_smem(sscan_bwd_kernel<T, true, sizeof(T) == 4>), prefer_smem(sscan_bwd_kernel<T, false, sizeof(T) == 4>), true);
-    (void)once;
+    prefer_smem(sscan_bwd_kernel<T, true, false>);    // remembered per (kernel, device)
+    prefer_smem(sscan_bwd_kernel<T, false, false>);
+    prefer_smem(sscan_bwd_kernel<T, true, sizeof(T) == 4>);
+    prefer_smem(sscan_bwd_kernel<T, false, sizeof(T) == 4>);
     const long long nt = n_tasks(&q->f);
     const unsigned grid = (unsigned)((nt + WPB - 1) / WPB);
     RowMaps tm;
@@ -1120,7 +1122,8 @@ extern "C" int b200_sscan_bwd(const b200_sscan_bwd_params* q, b200_stream_t stre
     B200_REQUIRE(q->f.ckpt != nullptr, "b200_sscan_bwd: the forward checkpoints (f.ckpt) are required");
     B200_REQUIRE(q->dout && q->du && q->ddelta && q->dA && q->dB && q->dC, "b200_sscan_bwd: dout/du/ddelta/dA/dB/dC must be non-NULL");
     B200_REQUIRE((q->f.z == nullptr) == (q->dz == nullptr), "b200_sscan_bwd: dz must be given exactly when z is");
-    B200_REQUIRE(q->dout_group_div >= 1, "b200_sscan_bwd: dout_group_div must be >= 1");
+    B200_REQUIRE(q->dout_group_div >= 1 && q->f.n_groups % (int)q->dout_group_div == 0,
+                 "b200_sscan_bwd: dout_group_div must be >= 1 and divide n_groups");
     B200_REQUIRE(q->dB_state_stride >= q->f.seqlen && q->dC_state_stride >= q->f.seqlen &&
                      (long long)q->f.dstate * q->dB_state_stride < (1ll << 31) && (long long)q->f.dstate * q->dC_state_stride < (1ll << 31),
                  "b200_sscan_bwd: dB/dC state strides must be in [seqlen, 2^31 / dstate)");

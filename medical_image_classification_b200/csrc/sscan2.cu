@@ -255,7 +255,11 @@ constexpr int CPWB = WB / TC;      // chunks per window
 constexpr int NSTB = 2;            // ring stages: a stage is refilled once its window's stores have left it
 constexpr int EXS = 24;            // exchange tiles: words per scan step (16 used; 24 keeps the STS.64 conflict free)
 constexpr int RDS = 144;           // state-reduction tile: words per state quad
+constexpr int CKP = 4 * TR + 16;      // checkpoint tile: words per state quad (64 + 16: the two quads of a half-warp hit disjoint banks)
 constexpr float kLn2 = 0.6931471805599453f;
+#ifndef B200_BWD_REGS
+#define B200_BWD_REGS 168   // 3 warps per SM sub-partition (16 K registers each): 12 per SM, one wave at the stage-0 shape
+#endif
 #ifndef B200_BWD_PRIV
 #define B200_BWD_PRIV 2
 #endif
@@ -278,7 +282,9 @@ struct __align__(1024) BwdSmem {
     float exd[TC * EXS];                // delta'
     float exg[TC * EXS];                // dout
     float2 priv[PRIV_SLOTS][4][32];     // per-lane accumulators that do not fit in registers: running dA (and the adjoint carry)
+    float ck[2][4 * CKP];               // [chunk parity] state entering the chunk: [state quad (pitch CKP)][state][row pair][2]
     uint64_t bar[NSTB];
+    uint64_t ckbar[2];
 };
 
 __device__ __forceinline__ int rd_pos(int quad, int cc, int i) { return quad * RDS + ((cc * 16 + 2 * i) ^ (((cc >> 1) & 1) << 4)); }
@@ -307,12 +313,13 @@ struct BwdChunkCtx {
 //   0: park = partner(i ^ 4)'s sums        1: park = partner(i ^ 2)'s (sums + park)
 //   2: park += partner(i ^ 4)'s sums       3: park += sums
 template <int MODE>
-__device__ __forceinline__ void bwd_state(BwdChunkCtx& cx, const float* pB, const float* pC, const float2 A2j, const float2 xm1,
+__device__ __forceinline__ void bwd_state(BwdChunkCtx& cx, const float* bB, const float* bC, const int off, const float2 A2j, const float2 xm1,
                                           float2& hj, float2& dAj, float (&park)[2 * TC]) {
+    // B / C of this state in scan order: 4 steps at word `off` of the tile (or reversed copy) bB / bC, the other 4 at off ^ 4
     float Bv[TC], Cv[TC];
     {
-        const float4 lo = *reinterpret_cast<const float4*>(pB);
-        const float4 hi = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>((reinterpret_cast<uintptr_t>(pB)) ^ 16));
+        const float4 lo = *reinterpret_cast<const float4*>(bB + off);
+        const float4 hi = *reinterpret_cast<const float4*>(bB + (off ^ 4));
         Bv[0] = lo.x; Bv[1] = lo.y; Bv[2] = lo.z; Bv[3] = lo.w; Bv[4] = hi.x; Bv[5] = hi.y; Bv[6] = hi.z; Bv[7] = hi.w;
     }
     float2 a[TC], x[TC];
@@ -326,8 +333,8 @@ __device__ __forceinline__ void bwd_state(BwdChunkCtx& cx, const float* pB, cons
         }
     }
     {
-        const float4 lo = *reinterpret_cast<const float4*>(pC);
-        const float4 hi = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>((reinterpret_cast<uintptr_t>(pC)) ^ 16));
+        const float4 lo = *reinterpret_cast<const float4*>(bC + off);
+        const float4 hi = *reinterpret_cast<const float4*>(bC + (off ^ 4));
         Cv[0] = lo.x; Cv[1] = lo.y; Cv[2] = lo.z; Cv[3] = lo.w; Cv[4] = hi.x; Cv[5] = hi.y; Cv[6] = hi.z; Cv[7] = hi.w;
     }
     float2 gn = hj, dAp = make_float2(0.f, 0.f);
@@ -359,23 +366,23 @@ __device__ __forceinline__ void bwd_state(BwdChunkCtx& cx, const float* pB, cons
 }
 
 template <int MODE, int J>
-__device__ __forceinline__ void bwd_slot(BwdChunkCtx& cx, const float* pB, const float* pC, const float2 A2j, const float2 xm1, float2& hj,
-                                         float2& dAj, float2 (*priv)[4][32], int lane, float (&park)[2 * TC]) {
+__device__ __forceinline__ void bwd_slot(BwdChunkCtx& cx, const float* pB, const float* pC, const int off, const float2 A2j, const float2 xm1,
+                                         float2& hj, float2& dAj, float2 (*priv)[4][32], int lane, float (&park)[2 * TC]) {
     if (PRIV_SLOTS == 0) {
-        bwd_state<MODE>(cx, pB, pC, A2j, xm1, hj, dAj, park);
+        bwd_state<MODE>(cx, pB, pC, off, A2j, xm1, hj, dAj, park);
     } else if (PRIV_SLOTS == 1) {
         float2 dA = make_float2(0.f, 0.f);
-        bwd_state<MODE>(cx, pB, pC, A2j, xm1, hj, dA, park);
+        bwd_state<MODE>(cx, pB, pC, off, A2j, xm1, hj, dA, park);
         priv[0][J][lane] = __fadd2_rn(priv[0][J][lane], dA);
     } else {
         float2 dA = make_float2(0.f, 0.f), h = priv[1][J][lane];
-        bwd_state<MODE>(cx, pB, pC, A2j, xm1, h, dA, park);
+        bwd_state<MODE>(cx, pB, pC, off, PRIV_SLOTS >= 3 ? priv[2][J][lane] : A2j, xm1, h, dA, park);
         priv[1][J][lane] = h;
         priv[0][J][lane] = __fadd2_rn(priv[0][J][lane], dA);
     }
 }
 
-__global__ void __maxnreg__(184)
+__global__ void __maxnreg__(B200_BWD_REGS)
 sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_constant__ BwdMaps tm, const unsigned tx_bytes,
                   const int zero_fill) {
     __shared__ BwdSmem sm;
@@ -403,6 +410,8 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < NSTB; ++s) mbar_init(&sm.bar[s], 1);
+        mbar_init(&sm.ckbar[0], 1);
+        mbar_init(&sm.ckbar[1], 1);
         mbar_init_fence();
     }
     __syncwarp();
@@ -428,17 +437,15 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
 
     // ---- per-lane constants and accumulators ----
     float2 A2[4], hh[4], dAacc[4];
-    int nst[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int n = 4 * sq + (j ^ pm);
-        nst[j] = n;
         A2[j].x = (okA && n < N) ? __ldg(p.A + (size_t)chA * N + n) * kLog2e : 0.f;
         A2[j].y = (okB && n < N) ? __ldg(p.A + (size_t)chB * N + n) * kLog2e : 0.f;
         hh[j] = make_float2(0.f, 0.f);
         dAacc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < PRIV_SLOTS; ++k) sm.priv[k][j][lane] = make_float2(0.f, 0.f);   // private to this lane: no synchronisation
+        for (int k = 0; k < PRIV_SLOTS; ++k) sm.priv[k][j][lane] = k == 2 ? A2[j] : make_float2(0.f, 0.f);   // private to this lane: no synchronisation
     }
     const float biasA = (p.delta_bias && okA) ? __ldg(p.delta_bias + chA) : 0.f;
     const float biasB = (p.delta_bias && okB) ? __ldg(p.delta_bias + chB) : 0.f;
@@ -446,7 +453,17 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
     const float DB = (p.D && okB) ? __ldg(p.D + chB) : 0.f;
     const bool softplus = p.delta_softplus != 0;
     float dD_A = 0.f, dD_B = 0.f, dbias_A = 0.f, dbias_B = 0.f;
-    const float* ck = p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR + 2 * i;
+    const float* ck = p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR;
+    // checkpoint of the state entering chunk c (c >= 1): 1 KB record -> tile ck[c & 1], one 256-byte bulk copy per state quad
+    auto issue_ck = [&](int c) {
+        const float* src = ck + (size_t)(c - 1) * NS * TR;
+        uint64_t* bar = &sm.ckbar[c & 1];
+        mbar_expect_tx(bar, NS * TR * 4);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) bulk_load_1d(&sm.ck[c & 1][qd * CKP], src + qd * 4 * TR, 4 * TR * 4, bar);
+    };
+    if (lane == 0 && nck > 1) issue_ck(nck - 1);
+    int ck_uses = 0;   // completed waits on the checkpoint barriers (chunks are visited in descending order: parity alternates)
 
     const int c0 = 2 * sq;                                           // this lane's two memory columns of every chunk
     const int st0 = rev ? TC - 1 - c0 : c0, st1 = rev ? TC - 2 - c0 : c0 + 1;   // their scan steps
@@ -469,10 +486,12 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
             const int jw = rev ? CPWB - 1 - k : k;       // its 32-byte slot inside the window rows
             const int la = (rev ? L - (c + 1) * TC : c * TC) + c0;
             const bool v01 = (unsigned)la < (unsigned)L; // L % 4 == 0 and c0 even: both columns in or both out
-            // checkpoint of the state entering this chunk (zero for the first), fetched one slot ahead of its use
-            const float* ckc = ck + (size_t)(c > 0 ? c - 1 : 0) * NS * TR;
-            auto load_ck = [&](int j) { return c > 0 ? __ldcs(reinterpret_cast<const float2*>(ckc + nst[j] * TR)) : make_float2(0.f, 0.f); };
-            float2 xcur, xnext = load_ck(3);
+            // checkpoint of the state entering this chunk: prefetched by a bulk copy while the previous chunk was computed
+            if (lane == 0 && c > 1) issue_ck(c - 1);     // tile (c - 1) & 1 was last read two chunks ago
+            if (c > 0) mbar_wait(&sm.ckbar[c & 1], (ck_uses >> 1) & 1);
+            ck_uses += c > 0;
+            const float* ckt = &sm.ck[c & 1][sq * CKP + 2 * i];
+            auto load_ck = [&](int j) { return c > 0 ? *reinterpret_cast<const float2*>(ckt + (j ^ pm) * TR) : make_float2(0.f, 0.f); };
             const int own = (((2 * jw + (sq >> 1)) ^ rkey) << 2) + 2 * (sq & 1);   // word offset of (c0, c0 + 1) inside a tile row
             const int offA = i * WB + own, offB = (i + 8) * WB + own;
             {   // ---- prologue (once per element): delta', its sigmoid, delta' * u ----
@@ -516,24 +535,23 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
                 cx.s1[cc] = make_float2(0.f, 0.f);
                 cx.s2[cc] = make_float2(0.f, 0.f);
             }
-            // B / C rows of slot j in scan order: first 16-byte half at p, the second at p ^ 16 bytes (both layouts)
-            auto bc_ptr = [&](const float* tile, const float* rv, int j) -> const float* {
-                const int n = nst[j];
-                return rev ? rv + n * TC : tile + n * WB + (((2 * jw) ^ ((n >> 1) & 3)) << 2);
+            // B / C rows of slot j in scan order: 4 steps at word offset bc_off(j) of the window tile (or of the reversed copy),
+            // the other 4 at bc_off(j) ^ 4
+            const float* bB = rev ? sm.un.a.rvs[0] : wB;
+            const float* bC = rev ? sm.un.a.rvs[1] : wC;
+            auto bc_off = [&](int j) {
+                const int n = 4 * sq + (j ^ pm);
+                return rev ? n * TC : n * WB + (((2 * jw) ^ ((n >> 1) & 3)) << 2);
             };
             float park[2 * TC];
             // slot 3: its sums go to the partner i ^ 4, whose slot 3 is this lane's slot 1
-            xcur = xnext; xnext = load_ck(1);
-            bwd_slot<0, 3>(cx, bc_ptr(wB, sm.un.a.rvs[0], 3), bc_ptr(wC, sm.un.a.rvs[1], 3), A2[3], xcur, hh[3], dAacc[3], sm.priv, lane, park);
+            bwd_slot<0, 3>(cx, bB, bC, bc_off(3), A2[3], load_ck(3), hh[3], dAacc[3], sm.priv, lane, park);
             // slot 1 (+ the partner's slot 3), then to the partner i ^ 2, whose slot 1 is this lane's slot 0
-            xcur = xnext; xnext = load_ck(2);
-            bwd_slot<1, 1>(cx, bc_ptr(wB, sm.un.a.rvs[0], 1), bc_ptr(wC, sm.un.a.rvs[1], 1), A2[1], xcur, hh[1], dAacc[1], sm.priv, lane, park);
+            bwd_slot<1, 1>(cx, bB, bC, bc_off(1), A2[1], load_ck(1), hh[1], dAacc[1], sm.priv, lane, park);
             // slot 2: to the partner i ^ 4, whose slot 2 is this lane's slot 0
-            xcur = xnext; xnext = load_ck(0);
-            bwd_slot<2, 2>(cx, bc_ptr(wB, sm.un.a.rvs[0], 2), bc_ptr(wC, sm.un.a.rvs[1], 2), A2[2], xcur, hh[2], dAacc[2], sm.priv, lane, park);
+            bwd_slot<2, 2>(cx, bB, bC, bc_off(2), A2[2], load_ck(2), hh[2], dAacc[2], sm.priv, lane, park);
             // slot 0: totals over lanes {i, i^2, i^4, i^6}; the last round, over steps, with the partner i ^ 1
-            xcur = xnext;
-            bwd_slot<3, 0>(cx, bc_ptr(wB, sm.un.a.rvs[0], 0), bc_ptr(wC, sm.un.a.rvs[1], 0), A2[0], xcur, hh[0], dAacc[0], sm.priv, lane, park);
+            bwd_slot<3, 0>(cx, bB, bC, bc_off(0), A2[0], load_ck(0), hh[0], dAacc[0], sm.priv, lane, park);
             float kB[4], kC[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -541,8 +559,8 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
                 kC[e] = (b0 ? park[TC + 4 + e] : park[TC + e]) + __shfl_xor_sync(0xffffffffu, b0 ? park[TC + e] : park[TC + 4 + e], 1);
             }
             __syncwarp();   // every lane has read this chunk's B / C, exq and the reversed copies
-            {   // dB / dC of state nst[0], scan steps 4 b0 .. 4 b0 + 3, written where B / C of those steps were
-                const int n = nst[0];
+            {   // dB / dC of state 4 sq + pm (slot 0), scan steps 4 b0 .. 4 b0 + 3, written where B / C of those steps were
+                const int n = 4 * sq + pm;
                 const int half = rev ? 1 - b0 : b0;
                 const int dst = n * WB + (((2 * jw + half) ^ ((n >> 1) & 3)) << 2);
                 const float4 vb = rev ? make_float4(kB[3], kB[2], kB[1], kB[0]) : make_float4(kB[0], kB[1], kB[2], kB[3]);
@@ -579,18 +597,46 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
             __syncwarp();   // the union (rd) and the exchange tiles are free for the next chunk
         }
         // ---- the window's outputs leave from its own tiles ----
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            const int l_lo = win_lo(v);
-            tma_store_4d(&tm.du, wu, l_lo, r0, g, b);
-            tma_store_4d(&tm.ddelta, wd, l_lo, r0, g, b);
-            tma_reduce_add_4d(&tm.dB, wB, l_lo, 0, g, b);
-            tma_reduce_add_4d(&tm.dC, wC, l_lo, 0, g, b);
-            tma_commit_group();
-            if (v + NSTB < nwin) {
-                tma_wait_read<0>();   // the stores have left the stage: refill it
+        const int l_lo = win_lo(v);
+        if (l_lo < 0) {
+            // TMA stores / reductions fault on negative coordinates (loads zero-fill them): the one window of a reversed group
+            // that hangs over position 0 (L % 16 != 0) is written element by element -- once per task.
+            __syncwarp();
+            const int nrows = min(TR, rpg - r0);
+#pragma unroll 1
+            for (int e = lane; e < TR * WB; e += 32) {
+                const int row = e >> 4, col = e & 15, l = l_lo + col;
+                const int off = row * WB + (((col >> 2) ^ ((row >> 1) & 3)) << 2) + (col & 3);
+                if (l >= 0 && l < L) {
+                    if (row < nrows) {
+                        ((float*)q.du)[(size_t)b * q.du_batch_stride + (size_t)(g * rpg + r0 + row) * q.du_row_stride + l] = wu[off];
+                        ((float*)q.ddelta)[(size_t)b * q.ddelta_batch_stride + (size_t)g * q.ddelta_group_stride +
+                                           (size_t)(r0 + row) * q.ddelta_row_stride + l] = wd[off];
+                    }
+                    if (row < N) {
+                        atomicAdd(q.dB + (size_t)b * q.dB_batch_stride + (size_t)g * q.dB_group_stride + (size_t)row * q.dB_state_stride + l, wB[off]);
+                        atomicAdd(q.dC + (size_t)b * q.dC_batch_stride + (size_t)g * q.dC_group_stride + (size_t)row * q.dC_state_stride + l, wC[off]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && v + NSTB < nwin) {
+                fence_proxy_async();
                 issue(v + NSTB);
+            }
+        } else {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_4d(&tm.du, wu, l_lo, r0, g, b);
+                tma_store_4d(&tm.ddelta, wd, l_lo, r0, g, b);
+                tma_reduce_add_4d(&tm.dB, wB, l_lo, 0, g, b);
+                tma_reduce_add_4d(&tm.dC, wC, l_lo, 0, g, b);
+                tma_commit_group();
+                if (v + NSTB < nwin) {
+                    tma_wait_read<0>();   // the stores have left the stage: refill it
+                    issue(v + NSTB);
+                }
             }
         }
     }
@@ -598,7 +644,7 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int n = nst[j];
+        const int n = 4 * sq + (j ^ pm);
         if (n < N) {
             const float2 dAv = PRIV_SLOTS >= 1 ? sm.priv[0][j][lane] : dAacc[j];
             if (okA) atomicAdd(q.dA + (size_t)chA * N + n, dAv.x);
@@ -671,9 +717,8 @@ bool try_fwd(const b200_sscan_fwd_params* p, cudaStream_t st, int* rc) {
     if (!make_fwd_maps(&tm, p, &tx, &zf)) return false;
     const int rpg = p->dim / p->n_groups;
     const long long nt = (long long)p->batch * p->n_groups * ((rpg + TR - 1) / TR);
-    static const bool once = (cudaFuncSetAttribute(sscan_fwd2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
-                              cudaFuncSetAttribute(sscan_fwd2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
-    (void)once;
+    (void)func_attr_per_device((const void*)sscan_fwd2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    (void)func_attr_per_device((const void*)sscan_fwd2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (p->z) sscan_fwd2_kernel<true><<<(unsigned)nt, 32, 0, st>>>(*p, tm, tx, zf);
     else sscan_fwd2_kernel<false><<<(unsigned)nt, 32, 0, st>>>(*p, tm, tx, zf);
     *rc = check_launch("sscan_fwd2_kernel");
@@ -719,8 +764,7 @@ bool try_bwd(const b200_sscan_bwd_params* q, cudaStream_t st, int* rc) {
     if (!make_bwd_maps(&tm, q, &tx, &zf)) return false;
     const int rpg = p->dim / p->n_groups;
     const long long nt = (long long)p->batch * p->n_groups * ((rpg + TR - 1) / TR);
-    static const bool once = (cudaFuncSetAttribute(sscan_bwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), true);
-    (void)once;
+    (void)func_attr_per_device((const void*)sscan_bwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     sscan_bwd2_kernel<<<(unsigned)nt, 32, 0, st>>>(*q, tm, tx, zf);
     *rc = check_launch("sscan_bwd2_kernel");
     return true;

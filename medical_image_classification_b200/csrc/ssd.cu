@@ -14,8 +14,8 @@
 // 128x64x32 tiles, operands staged global -> registers -> shared with the decay / dt' factors
 // applied on the way in, TF32 mma with the 3xTF32 split (hi*hi + hi*lo + lo*hi, fp32 accumulate)
 // so that fp32 callers get fp32-accurate products (precision = 0), or a single TF32 pass
-// (precision = 1: what the reference's tl.dot does on fp32 inputs).  These are warp-level mma.sync tiles
-// (HMMA in SASS), not yet tcgen05 / TMEM: DESIGN.md lists that as the next step for this operator.
+// (precision = 1: what the reference's tl.dot does on fp32 inputs).  Two interchangeable engines run the tiles: tcgen05.mma with
+// TMEM accumulators (TcEngine, the default; UTCHMMA / LDTM in SASS) and warp-level mma.sync tiles (MmaEngine, HMMA in SASS).
 // The backward is the exact adjoint of the chunked forward; it re-uses the forward's dt', cs,
 // chunk-entry states and C B^T (workspace) and the forward output (for the "stable" d cs term).
 #include <cstddef>
@@ -1478,17 +1478,12 @@ static int validate(const b200_ssd_fwd_params* p) {
 
 template <class K>
 static int set_smem(K kernel, size_t bytes = sizeof(Smem)) {
-    static thread_local const void* done[64];
-    static thread_local int ndone = 0;
-    for (int i = 0; i < ndone; ++i)
-        if (done[i] == (const void*)kernel) return 0;
     bytes = sizeof(tc::Shared) > sizeof(Smem) ? sizeof(tc::Shared) : sizeof(Smem);   // upper bound only; occupancy follows the launch's size
-    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    const cudaError_t e = func_attr_per_device((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);   // per (kernel, device)
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         return (int)e;
     }
-    if (ndone < 64) done[ndone++] = (const void*)kernel;
     return 0;
 }
 

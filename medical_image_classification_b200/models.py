@@ -11,8 +11,10 @@ from __future__ import annotations
 from functools import partial
 
 import torch
+
 import torch.nn as nn
 
+from ._lib import no_autocast as _no_autocast
 from .ss2d import SS2D, split_halves
 from .ss2d_ssd import SS2D_with_SSD
 
@@ -36,10 +38,10 @@ class DropPath(nn.Module):
 
 
 def _layer_norm(x, norm):
-    """nn.LayerNorm over the last dimension; on CUDA through libb200ssm's row kernel (csrc/lngate.cu), whose backward
+    """nn.LayerNorm over the last dimension through libb200ssm's row kernel (csrc/lngate.cu), whose backward
     replaces PyTorch's gamma/beta reduction (3.9 % of the step at 200 K rows x 96 channels).  Output dtype follows
     autocast like F.layer_norm's consumer would see it (fp32 without autocast)."""
-    if x.is_cuda and isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and x.shape[-1] <= 1024 and x.dtype in (torch.float32, torch.bfloat16):
+    if isinstance(norm, nn.LayerNorm) and norm.elementwise_affine and x.shape[-1] <= 1024 and x.dtype in (torch.float32, torch.bfloat16):
         from .ss2d import LnGateFn
         x = x.contiguous()   # rows contiguous (no-op when already so); fp32 or bf16 rows are read as they are
         return LnGateFn.apply(x, None, norm.weight, norm.bias, norm.eps, torch.float32)
@@ -88,6 +90,7 @@ class ShuffleCatAddFn(torch.autograd.Function):
     stream and both branches are bf16 (stages 1-3 of an autocast model)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, left, x, inp):
         from . import _lib
         _lib.require_cuda(left, x, inp)
@@ -108,6 +111,7 @@ class ShuffleCatAddFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dout):
         from . import _lib
         lib = _lib.load()
@@ -146,7 +150,7 @@ class SS_Conv_SSM(nn.Module):
 
     def forward(self, input):
         left, right = split_halves(input)
-        if right.is_cuda and right.dtype in (torch.float32, torch.bfloat16) and isinstance(self.ln_1, nn.LayerNorm) and right.shape[-1] <= 1024:
+        if right.dtype in (torch.float32, torch.bfloat16) and isinstance(self.ln_1, nn.LayerNorm) and right.shape[-1] <= 1024:
             from .ss2d import layer_norm_rows
             normed = layer_norm_rows(right, self.ln_1)     # pre-norm, the right half read in place (csrc/lngate.cu)
         else:
@@ -155,9 +159,9 @@ class SS_Conv_SSM(nn.Module):
         # the conv branch consumes channels-last data: on CUDA keep it in torch.channels_last (cuDNN / BatchNorm run NHWC
         # natively: no NCHW<->NHWC converter kernels; measured 33.2 -> 29.2 ms per MedMamba-T step)
         left = left.permute(0, 3, 1, 2)
-        left = left.contiguous(memory_format=torch.channels_last) if input.is_cuda else left.contiguous()
+        left = left.contiguous(memory_format=torch.channels_last)
         left = self.conv33conv33conv11(left)
-        if (input.is_cuda and input.dtype in (torch.float32, torch.bfloat16) and left.dtype in (torch.float32, torch.bfloat16)
+        if (input.dtype in (torch.float32, torch.bfloat16) and left.dtype in (torch.float32, torch.bfloat16)
                 and x.dtype in (torch.float32, torch.bfloat16) and left.shape[0] <= 65535):
             return ShuffleCatAddFn.apply(left, x, input)   # cat + channel shuffle + residual in one pass (csrc/glue.cu)
         left = left.permute(0, 2, 3, 1)

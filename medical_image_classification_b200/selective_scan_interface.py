@@ -21,6 +21,8 @@ import ctypes as C
 
 import torch
 
+
+from ._lib import no_autocast as _no_autocast
 from . import _lib
 
 CKPT_EVERY = 8  # steps between state checkpoints written by the forward for the recompute backward
@@ -171,6 +173,7 @@ class SelectiveScanFn(torch.autograd.Function):
     """Mirror of reference SelectiveScanFn (selective_scan_interface.py:20-80)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                 return_last_state=False, rev_mask=0, u_group_div=1):
         _check_inputs(u, delta, A, B, C, D, z, delta_bias, u_group_div)
@@ -207,6 +210,7 @@ class SelectiveScanFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dout, *args):
         u, delta, A32, Bm, Cm, D32, z, bias32, ckpt = ctx.saved_tensors
         dout = _last_contig(dout.to(u.dtype))

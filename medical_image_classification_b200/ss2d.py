@@ -16,9 +16,12 @@ from __future__ import annotations
 import math
 
 import torch
+
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
+from ._lib import no_autocast as _no_autocast
 from .cross import cross_scan_pack, scan_merge, ss2d_core  # noqa: F401
 from .selective_scan_interface import selective_scan_fn
 
@@ -44,6 +47,7 @@ class _ProjFn(torch.autograd.Function):
     fp32 operands keeps more mantissa (10 bits vs 8) and needs no casts; `tf32=False` is exact fp32 (parity tests)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, W, X, tf32):
         ctx.save_for_backward(W, X)
         ctx.tf32 = bool(tf32)
@@ -51,6 +55,7 @@ class _ProjFn(torch.autograd.Function):
             return torch.matmul(W, X)
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, g):
         W, X = ctx.saved_tensors
         dW = dX = None
@@ -82,18 +87,20 @@ class SplitHalvesFn(torch.autograd.Function):
     instead of two zero-filled full-size buffers, two slice copies and an add."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, inp):
         c = inp.shape[-1] // 2
         return inp[..., :c], inp[..., c:]
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dl, dr):
         return torch.cat((dl, dr.to(dl.dtype)), dim=-1)
 
 
 def split_halves(t):
-    """t.chunk(2, dim=-1); on CUDA with an even last dimension through SplitHalvesFn (one cat in the backward)."""
-    if t.is_cuda and t.shape[-1] % 2 == 0 and t.requires_grad:
+    """t.chunk(2, dim=-1); with an even last dimension through SplitHalvesFn (one cat in the backward)."""
+    if t.shape[-1] % 2 == 0 and t.requires_grad:
         return SplitHalvesFn.apply(t)
     return t.chunk(2, dim=-1)
 
@@ -105,6 +112,7 @@ class LnGateFn(torch.autograd.Function):
     chunk) and are read in place; returns out_dtype; dy comes back in y's dtype."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, y, z, weight, bias, eps, out_dtype):
         from . import _lib
         _lib.require_cuda(y, z, weight, bias)
@@ -134,6 +142,7 @@ class LnGateFn(torch.autograd.Function):
         return out.view(*y.shape[:-1], D)
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dout):
         from . import _lib
         lib = _lib.load()
@@ -160,6 +169,7 @@ class DwConvSiluFn(torch.autograd.Function):
     place (csrc/dwconv.cu) -- reference MedMamba.py:470-473 + the .float() of :403."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, xin, weight, bias):
         from . import _lib
         _lib.require_cuda(xin, weight, bias)
@@ -180,6 +190,7 @@ class DwConvSiluFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, g):
         from . import _lib
         lib = _lib.load()
@@ -318,17 +329,18 @@ class SS2D(nn.Module):
         B, H, W, C = x.shape
         xz = self.in_proj(x)
         x, z = split_halves(xz)
-        if (x.is_cuda and self.d_conv == 3 and W <= 64 and x.dtype in (torch.float32, torch.bfloat16)
+        _lib.require_cuda(x)                                        # no CPU path: oracle/cpu_path.py holds the eager CPU tree
+        if (self.d_conv == 3 and W <= 64 and x.dtype in (torch.float32, torch.bfloat16)
                 and self.forward_core == self.forward_core_fused):
             x = DwConvSiluFn.apply(x, self.conv2d.weight, self.conv2d.bias)   # conv3x3 + SiLU, channels-last in -> fp32 planes out
-        else:   # the reference's ops (CPU data flow / API-path parity tests)
+        else:   # shapes outside the kernel's envelope / the API-path parity tests: the reference's two library ops
             x = x.permute(0, 3, 1, 2).contiguous()
             x = self.act(self.conv2d(x))
         y = self.forward_core(x)                                    # (B, H, W, D) fp32
         assert y.dtype == torch.float32
-        if y.is_cuda and self.d_inner <= 1024 and z.dtype in (torch.float32, torch.bfloat16):
+        if self.d_inner <= 1024 and z.dtype in (torch.float32, torch.bfloat16):
             y = ln_gate(y, z, self.out_norm)                        # out_norm + silu(z) gate, one pass (csrc/lngate.cu)
-        else:   # CPU data flow (oracle/cpu_path.py binds forward_core): the reference's two ops
+        else:   # wider than the row kernel holds in registers: the reference's two library ops
             y = self.out_norm(y)
             y = y * F.silu(z)
         out = self.out_proj(y)

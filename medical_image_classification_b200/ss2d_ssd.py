@@ -20,6 +20,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib
+from .cross import cross_scan4, ssd_merge4
+from .ss2d import DwConvSiluFn
 from .ssd_combined import RMSNormGated, mamba_chunk_scan_combined
 
 
@@ -76,21 +79,16 @@ class SS2D_with_SSD(nn.Module):
         d_mlp = (zxbcdt.shape[-1] - 2 * self.d_ssm - 2 * self.ngroups * self.d_state - self.nheads) // 2
         z0, x0, z, xBCdt = torch.split(
             zxbcdt, [d_mlp, d_mlp, self.d_ssm, self.d_ssm + 2 * self.ngroups * self.d_state + self.nheads], dim=-1)
-        if xBCdt.is_cuda and self.d_conv == 3 and W <= 64 and xBCdt.dtype in (torch.float32, torch.bfloat16):
-            from .ss2d import DwConvSiluFn                                              # conv3x3 + SiLU, channels-last slice in place -> fp32 planes
-            xBCdt = DwConvSiluFn.apply(xBCdt, self.conv2d.weight, self.conv2d.bias)    # (B, c, H, W)
-        else:
+        _lib.require_cuda(xBCdt)                                                        # no CPU path
+        if self.d_conv == 3 and W <= 64 and xBCdt.dtype in (torch.float32, torch.bfloat16):
+            xBCdt = DwConvSiluFn.apply(xBCdt, self.conv2d.weight, self.conv2d.bias)    # conv3x3 + SiLU, channels-last slice in place -> fp32 planes (B, c, H, W)
+        else:   # outside the kernel's envelope: the reference's library ops
             xBCdt = self.act(self.conv2d(xBCdt.permute(0, 3, 1, 2).contiguous()))       # (B, c, H, W)
 
         # cross-scan of x, B, C and dt (SSD/MedSSD.py:332-336)
         gn = self.ngroups * self.d_state
-        if xBCdt.is_cuda:   # one pass per component (csrc/cross.cu::cross_scan4_kernel), channel slices read in place
-            from .cross import cross_scan4
-            xs, Bs, Cs, dts = (cross_scan4(t) for t in torch.split(xBCdt, [self.d_ssm, gn, gn, self.nheads], dim=1))
-        else:
-            hwwh = torch.stack([xBCdt.reshape(B, -1, L), xBCdt.transpose(2, 3).reshape(B, -1, L)], dim=1)
-            xBCdts = torch.cat([hwwh, hwwh.flip(-1)], dim=1)                              # (B, 4, c, L)
-            xs, Bs, Cs, dts = torch.split(xBCdts, [self.d_ssm, gn, gn, self.nheads], dim=2)
+        # one pass per component (csrc/cross.cu::cross_scan4_kernel), channel slices read in place
+        xs, Bs, Cs, dts = (cross_scan4(t) for t in torch.split(xBCdt, [self.d_ssm, gn, gn, self.nheads], dim=1))
         # (b, l, k*d) views with L stride 1 -- never made contiguous (SSD/MedSSD.py:344-347)
         xs = xs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (-1, self.headdim))     # (B, L, 4*nheads, P)
         Bs = Bs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (self.ngroups, -1))     # (B, L, G, 4*N)
@@ -106,14 +104,7 @@ class SS2D_with_SSD(nn.Module):
         assert y.dtype == torch.float32
 
         # cross-merge in the (B, L, K, d) layout (SSD/MedSSD.py:380-391)
-        if y.is_cuda:
-            from .cross import ssd_merge4
-            out = ssd_merge4(y, H, W).view(B, H, W, -1)                                         # one gather pass (csrc/cross.cu)
-        else:
-            inv_y = y[:, :, 2:4].flip(1)
-            wh_y = y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
-            invwh_y = inv_y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
-            out = (y[:, :, 0] + inv_y[:, :, 0] + wh_y + invwh_y).view(B, H, W, -1)
+        out = ssd_merge4(y, H, W).view(B, H, W, -1)                                             # one gather pass (csrc/cross.cu)
 
         if self.rmsnorm:
             out = self.norm(out, z)

@@ -20,8 +20,10 @@ from __future__ import annotations
 import ctypes
 
 import torch
+
 import torch.nn.functional as F
 
+from ._lib import no_autocast as _no_autocast
 from . import _lib
 
 # 0: fp32-accurate tensor-core products (3xTF32 split, default); 1: single-pass TF32 (the arithmetic
@@ -67,6 +69,7 @@ def _f32c(t):
 
 class SsdChunkScanFn(torch.autograd.Function):
     @staticmethod
+    @_no_autocast
     def forward(ctx, x, dt, A, B, C, D, dt_bias, initial_states, chunk_size, dt_softplus, dt_limit, return_final_states):
         lib = _lib.load()
         batch, L, H, P = x.shape
@@ -95,6 +98,7 @@ class SsdChunkScanFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dout, *unused):
         lib = _lib.load()
         x, dt_, A32, B_, C_, D32, bias32, init32, out, ws = ctx.saved_tensors
@@ -185,6 +189,7 @@ class RmsNormGatedFn(torch.autograd.Function):
     """y = rmsnorm(x * silu(z)) * w over the last dimension (norm_before_gate=False, one group)."""
 
     @staticmethod
+    @_no_autocast
     def forward(ctx, x, z, w, eps):
         lib = _lib.load()
         _lib.require_cuda(x, z, w)
@@ -204,6 +209,7 @@ class RmsNormGatedFn(torch.autograd.Function):
         return y.view(shape).to(x.dtype)
 
     @staticmethod
+    @_no_autocast
     def backward(ctx, dy):
         lib = _lib.load()
         x2, z2, w32, rstd = ctx.saved_tensors

@@ -1,18 +1,28 @@
-"""oracle/cpu_path.py -- TEST INFRASTRUCTURE: the reference's CPU data flow for the SS2D hot path.
+"""oracle/cpu_path.py -- TEST INFRASTRUCTURE: the reference's CPU data flow as its own eager module tree.
 
-Used only by bench.py's `cpu_baseline` leg / `--impl reference` arm and by tests.  It restates
-`SS2D.forward_corev0` (reference MedMamba.py:386-424) and the merge at MedMamba.py:476-477 with
-plain PyTorch CPU ops -- stack / transpose / flip / cat / einsum exactly as the reference does --
-and binds `selective_scan_fn` to the C restatement of `selective_scan_ref` (oracle/sscan_oracle.c,
-OpenMP over rows) instead of the reference's pure-PyTorch loop, whose autograd backward needs
-minutes per image.  kind = "port".
+Used only by bench.py's `cpu_baseline` leg / `--impl reference` arm and by tests.  The product modules
+(medical_image_classification_b200/{ss2d,models}.py) have NO CPU path -- their forwards call libb200ssm and raise on CPU
+tensors.  This file holds the eager restatement instead: sub-classes that keep the product constructors (hence parameter names and
+shapes: a reference / product state_dict loads with strict=True) and replace every `forward` with the reference's own
+PyTorch CPU ops, line for line:
+
+  * CpuSS2D        -- SS2D.forward (reference MedMamba.py:466-483) and forward_corev0 (:386-424): stack / transpose / flip /
+                      cat cross-scan, the two einsums, four-direction scan, flip / transpose / add cross-merge, out_norm, gate;
+  * CpuSSConvSSM   -- SS_Conv_SSM.forward (:530-538) with channel_shuffle (:486-499);
+  * CpuPatchEmbed2D / CpuPatchMerging2D -- :160-169 / :186-212.
+
+`selective_scan_fn` is bound to the C restatement of `selective_scan_ref` (oracle/sscan_oracle.c, OpenMP over rows) instead
+of the reference's pure-PyTorch loop, whose autograd backward needs minutes per image: kind = "port".
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 import oracle
+from medical_image_classification_b200.models import PatchEmbed2D, PatchMerging2D, SS_Conv_SSM, channel_shuffle
+from medical_image_classification_b200.ss2d import SS2D
 
 
 class OracleSelectiveScanFn(torch.autograd.Function):
@@ -36,7 +46,7 @@ class OracleSelectiveScanFn(torch.autograd.Function):
 
 
 def ss2d_core_cpu(m, x):
-    """x (B, D, H, W) -> (B, H, W, D); `m` supplies the SS2D parameters (reference names)."""
+    """x (B, D, H, W) -> (B, H, W, D); `m` supplies the SS2D parameters (reference names).  MedMamba.py:386-424, 476-477."""
     B, D, H, W = x.shape
     L = H * W
     K = 4
@@ -56,12 +66,60 @@ def ss2d_core_cpu(m, x):
     return torch.transpose(y, 1, 2).contiguous().view(B, H, W, -1)
 
 
+class CpuSS2D(SS2D):
+    def forward(self, x, **kwargs):                       # MedMamba.py:466-483
+        xz = self.in_proj(x)
+        x, z = xz.chunk(2, dim=-1)
+        x = x.permute(0, 3, 1, 2).contiguous()
+        x = self.act(self.conv2d(x))
+        y = ss2d_core_cpu(self, x)
+        assert y.dtype == torch.float32
+        y = self.out_norm(y)
+        y = y * F.silu(z)
+        out = self.out_proj(y)
+        if self.dropout is not None:
+            out = self.dropout(out)
+        return out
+
+
+class CpuSSConvSSM(SS_Conv_SSM):
+    def forward(self, input):                             # MedMamba.py:530-538
+        left, right = input.chunk(2, dim=-1)
+        right = self.drop_path(self.self_attention(self.ln_1(right)))
+        left = left.permute(0, 3, 1, 2).contiguous()
+        left = self.conv33conv33conv11(left)
+        left = left.permute(0, 2, 3, 1).contiguous()
+        output = torch.cat((left, right), dim=-1)
+        output = channel_shuffle(output, groups=2)
+        return output + input
+
+
+class CpuPatchEmbed2D(PatchEmbed2D):
+    def forward(self, x):                                 # MedMamba.py:164-169
+        x = self.proj(x).permute(0, 2, 3, 1)
+        return self.norm(x) if self.norm is not None else x
+
+
+class CpuPatchMerging2D(PatchMerging2D):
+    def forward(self, x):                                 # MedMamba.py:186-212
+        B, H, W, C = x.shape
+        h2, w2 = H // 2, W // 2
+        parts = [x[:, i::2, j::2, :][:, :h2, :w2, :] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))]
+        x = torch.cat(parts, dim=-1).view(B, h2, w2, 4 * C)
+        return self.reduction(self.norm(x))
+
+
+_CPU_CLASS = {SS2D: CpuSS2D, SS_Conv_SSM: CpuSSConvSSM, PatchEmbed2D: CpuPatchEmbed2D, PatchMerging2D: CpuPatchMerging2D}
+
+
 def bind_cpu_core(model):
-    """Point every SS2D block of a (CPU) VSSM at the CPU data flow above."""
-    from functools import partial
+    """Turn a (CPU) product module tree into the eager CPU tree above: every module whose class has a Cpu twin is re-classed
+    (the twins add no attributes, only replace `forward`), parameters and buffers stay where they are.
+    Returns the number of SS2D blocks converted."""
     n = 0
     for mod in model.modules():
-        if hasattr(mod, "forward_core") and hasattr(mod, "x_proj_weight"):
-            mod.forward_core = partial(ss2d_core_cpu, mod)
-            n += 1
+        twin = _CPU_CLASS.get(type(mod))
+        if twin is not None:
+            mod.__class__ = twin
+            n += twin is CpuSS2D
     return n

@@ -44,8 +44,8 @@ def test_invalid_params_return_error_without_launching():
 
 def test_ckpt_bytes():
     lib = _lib.load()
-    # 2 batches x 4 groups x ceil(96/32)=3 tiles, L=3136 -> 391 stored chunks of 16x32 floats
-    assert lib.b200_sscan_ckpt_bytes(2, 384, 3136, 16, 4, 8) == 2 * 4 * 3 * 391 * 16 * 32 * 4
+    # 2 batches x 4 groups x ceil(96/16)=6 row tiles, L=3136 -> 391 stored chunks of 16 states x 16 rows floats
+    assert lib.b200_sscan_ckpt_bytes(2, 384, 3136, 16, 4, 8) == 2 * 4 * 6 * 391 * 16 * 16 * 4
 
 
 def test_no_cpu_fallback():

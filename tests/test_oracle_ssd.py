@@ -117,3 +117,93 @@ def test_backward_matches_torch_autograd(cfg):
             continue
         v = v.numpy()
         assert np.abs(gr[k] - v).max() / max(np.abs(v).max(), 1e-30) < 1e-6, k
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Cross-check against an INDEPENDENT implementation: transformers' pure-PyTorch Mamba-2 mixer
+# (transformers/models/mamba2/modeling_mamba2.py::Mamba2Mixer.torch_forward, the "ssd naive implementation" section).
+# mamba_ssm 2.2.2 itself is not installable here; this is the closest obtainable statement of what
+# mamba_chunk_scan_combined computes that the oracle's author did not write.
+# ------------------------------------------------------------------------------------------------------------------
+def _hf_mixer(L, heads, headdim, groups, dstate, chunk, seed):
+    m2 = pytest.importorskip("transformers.models.mamba2.modeling_mamba2")
+    cfg_cls = pytest.importorskip("transformers").Mamba2Config
+    cfg = cfg_cls(num_heads=heads, head_dim=headdim, hidden_size=heads * headdim // 2, state_size=dstate, expand=2, n_groups=groups,
+                  chunk_size=chunk, conv_kernel=4, num_hidden_layers=1, vocab_size=16, use_conv_bias=True, use_bias=False,
+                  time_step_limit=(0.0, float("inf")))
+    torch.manual_seed(seed)
+    mixer = m2.Mamba2Mixer(cfg, layer_idx=0).double().eval()
+    with torch.no_grad():
+        mixer.A_log.copy_(torch.log(torch.rand(heads, dtype=torch.float64) * 3 + 0.2))
+        mixer.D.copy_(torch.randn(heads, dtype=torch.float64))
+        mixer.dt_bias.copy_(torch.randn(heads, dtype=torch.float64) * 0.5)
+    return mixer
+
+
+@pytest.mark.parametrize("L,heads,headdim,groups,dstate,chunk", [(70, 4, 8, 1, 12, 32), (64, 4, 16, 2, 8, 16), (33, 2, 8, 1, 16, 256)])
+def test_oracle_matches_transformers_torch_forward(L, heads, headdim, groups, dstate, chunk):
+    mixer = _hf_mixer(L, heads, headdim, groups, dstate, chunk, seed=L)
+    torch.manual_seed(1)
+    hidden = torch.randn(2, L, heads * headdim // 2, dtype=torch.float64)
+    captured = {}
+    handle = mixer.norm.register_forward_pre_hook(lambda mod, args: captured.setdefault("y", args[0].detach().clone()))
+    with torch.no_grad():
+        mixer.torch_forward(hidden)
+    handle.remove()
+    # the operator's inputs, recomputed with the mixer's own layers (steps 1-2 of torch_forward)
+    with torch.no_grad():
+        proj = mixer.in_proj(hidden)
+        inter, gn = mixer.intermediate_size, mixer.n_groups * mixer.ssm_state_size
+        d_mlp = (proj.shape[-1] - 2 * inter - 2 * gn - mixer.num_heads) // 2
+        _, _, _gate, xBC, dt = proj.split([d_mlp, d_mlp, inter, mixer.conv_dim, mixer.num_heads], dim=-1)
+        xBC = mixer.act(mixer.conv1d(xBC.transpose(1, 2))[..., :L].transpose(1, 2))
+        x, Bm, Cm = torch.split(xBC, [inter, gn, gn], dim=-1)
+    x = x.reshape(2, L, heads, headdim)
+    Bm = Bm.reshape(2, L, groups, dstate)
+    Cm = Cm.reshape(2, L, groups, dstate)
+    A = -torch.exp(mixer.A_log.detach())
+    out, _ = oracle.ssd_fwd(x.numpy(), dt.numpy(), A.numpy(), Bm.numpy(), Cm.numpy(), D=mixer.D.detach().numpy(),
+                            dt_bias=mixer.dt_bias.detach().numpy(), dt_softplus=True)
+    y_hf = captured["y"].reshape(2, L, heads, headdim).numpy()
+    err = np.abs(out.astype(np.float64) - y_hf).max() / np.abs(y_hf).max()
+    assert err < 2e-6, err      # the oracle returns fp32 outputs of an fp64 recurrence
+
+
+def test_oracle_grads_match_transformers_autograd():
+    """All seven gradients of the operator (dx, ddt, dA, dB, dC, dD, ddt_bias) against torch autograd THROUGH transformers'
+    torch_forward: the loss only sees the SSD output (captured at the input of the mixer's gated norm), the gradients are read
+    at the operator's inputs (output of the conv activation; the dt columns of in_proj's output; A_log, D, dt_bias)."""
+    L, heads, headdim, groups, dstate, chunk = 50, 4, 8, 1, 12, 16
+    mixer = _hf_mixer(L, heads, headdim, groups, dstate, chunk, seed=7)
+    torch.manual_seed(2)
+    hidden = torch.randn(2, L, heads * headdim // 2, dtype=torch.float64)
+    cap = {}
+    hooks = [mixer.norm.register_forward_pre_hook(lambda mod, args: cap.setdefault("y", args[0])),
+             mixer.act.register_forward_hook(lambda mod, args, out: cap.setdefault("xBC", out)),
+             mixer.in_proj.register_forward_hook(lambda mod, args, out: cap.setdefault("proj", out))]
+    mixer.torch_forward(hidden)
+    for h in hooks:
+        h.remove()
+    y, xBC, proj = cap["y"], cap["xBC"], cap["proj"]
+    dout = torch.randn_like(y)
+    g_xBC, g_proj, g_Alog, g_D, g_bias = torch.autograd.grad((y * dout).sum(), [xBC, proj, mixer.A_log, mixer.D, mixer.dt_bias])
+    inter, gn = mixer.intermediate_size, groups * dstate
+    x, Bm, Cm = (t.detach() for t in torch.split(xBC[:, :L], [inter, gn, gn], dim=-1))
+    gx, gB, gC = torch.split(g_xBC[:, :L], [inter, gn, gn], dim=-1)
+    dt = proj.detach()[..., -heads:]
+    A = -torch.exp(mixer.A_log.detach())
+    g = oracle.ssd_bwd(x.reshape(2, L, heads, headdim).numpy(), dt.numpy(), A.numpy(), Bm.reshape(2, L, groups, dstate).numpy(),
+                       Cm.reshape(2, L, groups, dstate).numpy(), D=mixer.D.detach().numpy(), dt_bias=mixer.dt_bias.detach().numpy(),
+                       dt_softplus=True, dout=dout.reshape(2, L, heads, headdim).numpy())
+
+    def rel(a, b):
+        b = b.detach().numpy()
+        return np.abs(np.asarray(a, np.float64).reshape(b.shape) - b).max() / np.abs(b).max()
+
+    assert rel(g["dx"], gx.reshape(2, L, heads, headdim)) < 2e-6
+    assert rel(g["dB"], gB.reshape(2, L, groups, dstate)) < 2e-6
+    assert rel(g["dC"], gC.reshape(2, L, groups, dstate)) < 2e-6
+    assert rel(g["ddt"], g_proj[..., -heads:]) < 2e-6
+    assert rel(g["dA"] * A.numpy(), g_Alog) < 2e-6          # A = -exp(A_log)  =>  dA_log = dA * A
+    assert rel(g["dD"], g_D) < 2e-6
+    assert rel(g["ddt_bias"], g_bias) < 2e-6
