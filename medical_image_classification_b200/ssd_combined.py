@@ -40,8 +40,12 @@ def _effective_precision() -> int:
     return _precision
 
 
-def set_precision(mode: int) -> None:
+def set_precision(mode) -> None:
+    """0 / 1 fix the mode; None returns to the default policy (fp32-accurate, single-pass TF32 under autocast)."""
     global _precision, _explicit
+    if mode is None:
+        _precision, _explicit = 0, False
+        return
     if mode not in (0, 1):
         raise ValueError("precision must be 0 (3xTF32, fp32-accurate) or 1 (single-pass TF32)")
     _precision = mode

@@ -247,10 +247,65 @@ def atrous_case(name, B, C, H, W, seed=0):
     print("wrote atrous", name, tuple(xs.shape))
 
 
+def _grad_sample(t, n=4096):
+    """<= n evenly strided elements of a gradient (every parameter stays comparable without storing 6 M floats)."""
+    f = t.detach().flatten()
+    if f.numel() <= n:
+        return _np(f)
+    return _np(f[torch.arange(0, f.numel(), f.numel() // n)[:n]])
+
+
+def medmamba_real_dims_case(seed=0):
+    """fp32 goldens for the configuration bench.py benchmarks under bf16 autocast: the UNMODIFIED reference VSSM at MedMamba-T's
+    real widths (dims 96-192-384-768, d_state 16, 224 x 224 input; depths 1-1-1-1, batch 4 to keep the CPU run in minutes), with
+    `selective_scan_fn` bound to the C restatement of selective_scan_ref (oracle/sscan_oracle.c, itself pinned on the reference's
+    function by tests/test_oracle_golden.py; the reference's own autograd backward needs ~6 minutes per image at L = 3136).
+    Weights are NOT stored (6 M floats): they are the product model's seeded CPU initialisation, which the test re-creates;
+    `param_checksum` guards against RNG drift.  Gradients are stored as <= 4096 strided samples per parameter."""
+    from medical_image_classification_b200.models import VSSM as ProductVSSM
+    from oracle.cpu_path import OracleSelectiveScanFn
+
+    def scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, return_last_state=False):
+        assert z is None and not return_last_state
+        return OracleSelectiveScanFn.apply(u.contiguous(), delta.contiguous(), A.contiguous(), B.contiguous(), C.contiguous(), D, delta_bias,
+                                           delta_softplus)
+
+    mm = ref_import.load_medmamba(selective_scan_fn=scan_fn)
+    kw = dict(num_classes=6, depths=[1, 1, 1, 1], dims=[96, 192, 384, 768], drop_path_rate=0.0)
+    torch.manual_seed(seed)
+    prod = ProductVSSM(**kw)                        # CPU construction only: nothing is launched
+    net = mm.VSSM(**kw)
+    net.load_state_dict(prod.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(4, 3, 224, 224, generator=g)
+    y = torch.randint(0, 6, (4,), generator=g)
+    rec = {"y": _np(y), "seed": np.array(seed),
+           "param_checksum": np.array([float(sum(p.double().sum() for p in prod.parameters())),
+                                       float(sum(p.double().abs().sum() for p in prod.parameters()))])}
+    net.eval()
+    with torch.no_grad():
+        rec["logits_eval"] = _np(net(x))
+    net.train()
+    logits = net(x)
+    loss = torch.nn.functional.cross_entropy(logits, y)
+    loss.backward()
+    rec["logits_train"] = _np(logits)
+    rec["loss"] = _np(loss)
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            rec["grad." + k] = _grad_sample(p.grad)
+            rec["gnorm." + k] = np.array(float(p.grad.double().norm()))
+    np.savez_compressed(os.path.join(OUT, "medmamba_real_dims.npz"), **rec)
+    print("wrote medmamba_real_dims: loss", float(loss), "logits_eval[0]", rec["logits_eval"][0])
+
+
 def main():
     assert ref_import.available(), "/root/reference is not mounted"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--real-dims-only" in sys.argv:
+        medmamba_real_dims_case()
+        return
     if "--atrous-only" in sys.argv:
         atrous_case("8x8", 2, 3, 8, 8)
         atrous_case("7x9", 1, 5, 7, 9, seed=1)
@@ -281,6 +336,7 @@ def main():
     ss2d_ssd_case("d32_7x5", 32, 8, 16, 7, 5, 2)
     ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
     medssd_case()
+    medmamba_real_dims_case()
     crossmamba_case("d32_6x5", 32, 8, 16, 6, 5, 2)
     atrous_case("8x8", 2, 3, 8, 8)
     atrous_case("7x9", 1, 5, 7, 9, seed=1)
