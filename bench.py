@@ -31,12 +31,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "MedMamba-T train images/sec @224"
 UNIT = "images/s"
 PER_GPU_BATCH = 64
 NUM_CLASSES = 6
-WORKLOAD = ("MedMamba-T (VSSM depths 2-2-4-2, dims 96-768, 6 classes) bf16-autocast training step, "
-            "batch 64 per GPU, synthetic 3x224x224 (BASELINE.json configs[1])")
+REF_BATCH = 8      # BASELINE.json configs[0]: the reference's own CPU-runnable case is batch 8
+MODELS = {
+    # default: the configuration BASELINE.json's metric is quoted on (configs[1])
+    "medmamba_t": dict(metric="MedMamba-T train images/sec @224",
+                       workload=("MedMamba-T (VSSM depths 2-2-4-2, dims 96-768, 6 classes) bf16-autocast training step, "
+                                 "batch 64 per GPU, synthetic 3x224x224 (BASELINE.json configs[1])")),
+    # BASELINE.json configs[2]: the Mamba-2 SSD family
+    "medssd": dict(metric="MedSSD train images/sec @224",
+                   workload=("MedSSD (SSD/MedSSD.py VSSM depths 2-2-4-2, dims 128-1024, d_state 128 -> N' = 512, 6 classes) bf16-autocast "
+                             "training step, batch 64 per GPU, synthetic 3x224x224 (BASELINE.json configs[2])")),
+}
+METRIC = MODELS["medmamba_t"]["metric"]
+WORKLOAD = MODELS["medmamba_t"]["workload"]
+
+
+def build_model(name):
+    from medical_image_classification_b200 import models
+    return getattr(models, name)(num_classes=NUM_CLASSES)
 
 
 def peaks():
@@ -45,6 +60,15 @@ def peaks():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak_tf32():
+    """TF32 dense peak taken as half the measured sustained bf16 figure (the SSD kernels run inside a long step)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["bf16_tflops_sustained"]) / 2, "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2 = TF32)"
+    except Exception:
+        return 1400.0 / 2, "fallback (B200_PROFILING.md sustained bf16 1.4 PFLOP/s / 2 = TF32)"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -109,7 +133,8 @@ class ScanProfiler:
     def __init__(self):
         import torch
         from medical_image_classification_b200 import selective_scan_interface as ssi
-        self.torch, self.ssi = torch, ssi
+        from medical_image_classification_b200 import _lib
+        self.torch, self.ssi, self.lib = torch, ssi, _lib.load()
         self.records = []  # (key, bytes, start_event, end_event)
         self.enabled = False
 
@@ -121,7 +146,7 @@ class ScanProfiler:
         batch, KD, L = delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), delta.shape[-1]   # (B, KD, L) or a (B, K, D, L) view
         G, N = Bm.shape[1], Bm.shape[2]
         E, Ebc = batch * KD * L, batch * G * N * L
-        if kind == "fwd":
+        if kind.startswith("fwd"):
             return s * (3 * E + 2 * Ebc) + 4 * (KD * N + 2 * KD)
         return s * (5 * E + 2 * Ebc) + 4 * 2 * Ebc + 4 * (2 * KD * N + 4 * KD)
 
@@ -140,7 +165,8 @@ class ScanProfiler:
             return
         e1 = self.torch.cuda.Event(enable_timing=True)
         e1.record()
-        key = (kind, (delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), delta.shape[-1]), Bm.shape[2], str(u.dtype))
+        gen = "2" if self.lib.b200_sscan_last_variant() == 2 else ""
+        key = (kind + gen, (delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), delta.shape[-1]), Bm.shape[2], str(u.dtype))
         self.records.append((key, self.algorithmic_bytes(kind, u, delta, Bm), e0, e1))
 
     def summary(self, peak_gbs, peak_src, steps):
@@ -182,18 +208,93 @@ class ScanProfiler:
         return roof, allscan
 
 
+class SsdProfiler:
+    """Same idea for the SSD operator (b200_ssd_fwd / b200_ssd_bwd: 5 + 6 kernels per call): CUDA events immediately around the
+    C-ABI call, algorithmic FLOPs and bytes per call from SURVEY.md 8(d)."""
+
+    def __init__(self):
+        import torch
+        from medical_image_classification_b200 import ssd_combined
+        self.torch, self.mod = torch, ssd_combined
+        self.records, self.enabled = [], False
+
+    @staticmethod
+    def work(kind, batch, L, H, P, G, N, Q, s=4):
+        nq = [min(Q, L - c) for c in range(0, L, Q)]
+        if kind == "fwd":
+            flops = batch * sum(2 * q * q * N * G + H * (2 * q * q * P + 4 * q * N * P) for q in nq)
+            nbytes = s * (2 * batch * L * H * P + 2 * batch * L * G * N + batch * L * H)
+        else:
+            flops = batch * sum(6 * q * q * N * G + H * (4 * q * q * P + 10 * q * N * P) for q in nq)
+            nbytes = s * (3 * batch * L * H * P + 4 * batch * L * G * N + 2 * batch * L * H)
+        return flops, nbytes
+
+    def install(self):
+        self.mod.set_profiler(self)
+
+    def begin(self):
+        if not self.enabled:
+            return None
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return e0
+
+    def end(self, e0, kind, shape):
+        if e0 is None:
+            return
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append(((kind,) + tuple(shape), e0, e1))
+
+    def summary(self, hbm_peak, hbm_src, steps):
+        agg = {}
+        for key, e0, e1 in self.records:
+            a = agg.setdefault(key, [0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+        if not agg:
+            return None, None
+        tpk, tsrc = tensor_peak_tf32()
+        rows = []
+        for key, (n, ms) in agg.items():
+            kind, batch, L, H, P, G, N, Q, prec = key
+            flops, nbytes = self.work(kind, batch, L, H, P, G, N, Q)
+            t = ms / n
+            rows.append({"op": f"b200_ssd_{kind}", "shape_b_l_h_p_g_n_q": [batch, L, H, P, G, N, Q], "precision": "tf32" if prec else "3xtf32",
+                         "launches": n, "ms_per_call": round(t, 4), "flops_per_call": flops, "bytes_per_call": nbytes,
+                         "tflops": round(flops / t / 1e9, 2), "gbs": round(nbytes / t / 1e6, 1),
+                         "t_tensor_ms": round(flops / tpk / 1e9, 4), "t_hbm_ms": round(nbytes / hbm_peak / 1e6, 4)})
+        rows.sort(key=lambda r: -r["ms_per_call"] * r["launches"])
+        top = rows[0]
+        bound = "tensor" if top["t_tensor_ms"] >= top["t_hbm_ms"] else "hbm"
+        if bound == "tensor":
+            roof = {"bound": "tensor", "achieved": top["tflops"], "peak": tpk, "unit": "TFLOP/s", "frac": round(top["tflops"] / tpk, 4),
+                    "peak_source": tsrc}
+        else:
+            roof = {"bound": "hbm", "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": round(top["gbs"] / hbm_peak, 4),
+                    "peak_source": hbm_src}
+        roof.update({"kernel": top["op"] + " (all kernels of the call)", "shape_b_l_h_p_g_n_q": top["shape_b_l_h_p_g_n_q"],
+                     "precision": top["precision"], "ms_per_launch": top["ms_per_call"], "flops_per_launch": top["flops_per_call"],
+                     "bytes_per_launch": top["bytes_per_call"], "traffic": None,
+                     "formula": "SURVEY.md 8(d): max(HBM time, tensor time) of the SSD call; FLOPs sum_c 2 q^2 N G + H (2 q^2 P + 4 q N P) fwd, "
+                                "6 / 4 / 10 bwd; bytes at fp32 I/O"})
+        tot_ms = sum(r["ms_per_call"] * r["launches"] for r in rows)
+        allssd = {"calls_per_step": round(sum(r["launches"] for r in rows) / steps, 1), "ms_per_step": round(tot_ms / steps, 4),
+                  "tflops": round(sum(r["flops_per_call"] * r["launches"] for r in rows) / tot_ms / 1e9, 2), "per_call": rows}
+        return roof, allssd
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the reference's CPU data flow (port)
 # ------------------------------------------------------------------------------------------------
-def cpu_train_step_time(batch: int, steps: int = 1, warmup: int = 0, threads: int | None = None):
+def cpu_train_step_time(batch: int, steps: int = 1, warmup: int = 0, threads: int | None = None, model: str = "medmamba_t"):
     import torch
     import oracle
     from oracle.cpu_path import bind_cpu_core
-    from medical_image_classification_b200.models import medmamba_t
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    net = medmamba_t(num_classes=NUM_CLASSES)
+    net = build_model(model)
     bind_cpu_core(net)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
     x = torch.randn(batch, 3, 224, 224)
@@ -212,24 +313,24 @@ def cpu_train_step_time(batch: int, steps: int = 1, warmup: int = 0, threads: in
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port), all host
-    threads, each step a bounded sample (a small batch) of the same workload."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the eager CPU module tree of
+    oracle/cpu_path.py + the C restatements of selective_scan_ref / the SSD recurrence), all host threads.  Each step is a bounded
+    sample of the workload: ONE fixed batch -- --cpu-batch, default 8 = BASELINE.json configs[0] -- so the number is reproducible
+    from run to run and from N to N (round 1 picked the batch from a wall-clock heuristic)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = MODELS[args.model]
     cores = os.cpu_count() or 1
-    t1, threads = cpu_train_step_time(1, steps=1, warmup=0)          # calibration
-    budget = 150.0
-    n_steps = args.steps + args.warmup
-    b = int(max(1, min(8, budget / max(n_steps, 1) / max(t1, 1e-3))))
-    t, threads = cpu_train_step_time(b, steps=args.steps, warmup=args.warmup)
+    b = args.cpu_batch
+    t, threads = cpu_train_step_time(b, steps=args.steps, warmup=args.warmup, model=args.model)
     value = b / t
-    sample = (f"MedMamba-T fp32 fwd+bwd+Adam on batch {b} of synthetic 3x224x224 per step "
-              f"(PyTorch CPU ops + C/OpenMP restatement of selective_scan_ref), {threads} threads")
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+    sample = (f"{args.model} fp32 fwd+bwd+Adam on batch {b} of synthetic 3x224x224 per step "
+              f"(PyTorch CPU ops + C/OpenMP restatement of the scan), {threads} threads")
+    line = {"impl": "reference", "metric": cfg["metric"], "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "config": {"workload": cfg["workload"], "sample": sample, "cpu_batch": b},
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                              "host_cores": cores},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -264,81 +365,38 @@ def run_cuda(args):
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234 + rank)
 
+    cfg = MODELS[args.model]
     cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t, threads = cpu_train_step_time(args.cpu_batch, steps=1, warmup=0)
-        cpu_base = {"value": round(args.cpu_batch / t, 4), "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": f"one fp32 MedMamba-T training step (fwd+bwd+Adam) on batch {args.cpu_batch} of synthetic "
-                              f"3x224x224 (BASELINE.json configs[0]); PyTorch CPU ops + C/OpenMP restatement of "
-                              f"selective_scan_ref; {t:.1f} s",
+    if rank == 0 and not args.no_cpu_baseline:
+        # rank 0 times the CPU port at every N (before the other ranks' first collective: they wait at the barrier below)
+        cb = args.cpu_batch if args.model == "medmamba_t" else min(args.cpu_batch, 2)
+        t, threads = cpu_train_step_time(cb, steps=1, warmup=0, model=args.model)
+        cpu_base = {"value": round(cb / t, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"one fp32 {args.model} training step (fwd+bwd+Adam) on batch {cb} of synthetic "
+                              f"3x224x224 (BASELINE.json configs[0] is batch 8); PyTorch CPU ops + C/OpenMP restatement of "
+                              f"the scan; {t:.1f} s",
                     "host_cores": os.cpu_count()}
 
-    net = medmamba_t(num_classes=NUM_CLASSES).to(dev)
+    from medical_image_classification_b200.train_step import TrainStep
+    net = build_model(args.model).to(dev)
     use_graph = not args.no_graph
-    side = torch.cuda.Stream(device=dev)
-    if ddp:
-        with torch.cuda.stream(side):  # DDP built on the capture-warm-up stream (PyTorch CUDA-graph + DDP recipe)
-            model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
-        torch.cuda.current_stream().wait_stream(side)
-    else:
-        model = net
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=use_graph)
+    step = TrainStep(net, lr=1e-4, autocast=torch.bfloat16, ddp=ddp, local_rank=local_rank, graph=use_graph,
+                     bucket_cap_mb=args.bucket_mb, grad_bf16=args.grad_bf16)
+    model = step.model
     B = args.batch
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, NUM_CLASSES, (B,), device=dev)
     x_host = torch.randn(B, 3, 224, 224).pin_memory()
     y_host = torch.randint(0, NUM_CLASSES, (B,)).pin_memory()
+    eager_step, barrier = step.eager, step.barrier
 
-    def fwd_bwd_opt(x, y):
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = torch.nn.functional.cross_entropy(model(x).float(), y)
-        loss.backward()
-        opt.step()
-        return loss
-
-    def eager_step(x, y):
-        opt.zero_grad(set_to_none=True)
-        return fwd_bwd_opt(x, y)
-
-    def barrier():
-        if ddp:
-            dist.barrier(device_ids=[local_rank])
-        torch.cuda.synchronize(dev)
-
-    prof = ScanProfiler()
+    prof = ScanProfiler() if args.model == "medmamba_t" else SsdProfiler()
     prof.install()
-    # warm-up (also the >= 11 side-stream iterations DDP wants before a capture)
-    n_warm = max(args.warmup, 3, 11 if (use_graph and ddp) else 0)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(n_warm):
-            eager_step(x_dev, y_dev)
-    torch.cuda.current_stream().wait_stream(side)
-    barrier()
-
+    step.warmup(x_dev, y_dev, n=max(args.warmup, 3))
     # ---- capture the whole step (forward, loss, backward, Adam) in one CUDA graph ----
-    graph, static_x, static_y, static_loss, graph_note = None, None, None, None, "eager"
-    if use_graph:
-        try:
-            static_x, static_y = x_dev.clone(), y_dev.clone()
-            opt.zero_grad(set_to_none=True)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_loss = fwd_bwd_opt(static_x, static_y)
-            graph_note = "whole step captured in one CUDA graph"
-        except Exception as exc:  # keep measuring: fall back to eager launches and say so
-            graph, graph_note = None, f"eager (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
-            torch.cuda.synchronize(dev)
-            opt.zero_grad(set_to_none=True)
-
-    def run_step(x, y):
-        if graph is None:
-            return eager_step(x, y)
-        if x is not static_x:
-            static_x.copy_(x, non_blocking=True)
-            static_y.copy_(y, non_blocking=True)
-        graph.replay()
-        return static_loss
+    step.capture(x_dev, y_dev)
+    graph, static_x, static_y, graph_note = step.graph, step.static_x, step.static_y, step.note
+    run_step = step
 
     for _ in range(3):
         run_step(static_x if graph is not None else x_dev, static_y if graph is not None else y_dev)
@@ -394,7 +452,7 @@ def run_cuda(args):
     # ---- per-launch CUDA-event timing of the scan kernels: the same K steps, launched eagerly so the
     #      events bracket each kernel on its stream (events cannot be read back from a graph replay) ----
     kernel_launches_per_step = None
-    opt_e = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True) if graph is not None else opt
+    opt_e = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True) if graph is not None else step.opt
 
     def eager_probe(x, y):
         opt_e.zero_grad(set_to_none=True)
@@ -422,19 +480,22 @@ def run_cuda(args):
         peak, peak_src = peaks()
         roof, allscan = prof.summary(peak, peak_src, args.steps)
         total = B * world * args.steps
-        line = {"metric": METRIC, "value": round(total / (ms / 1e3), 2), "unit": UNIT, "n_gpus": world,
+        line = {"metric": cfg["metric"], "value": round(total / (ms / 1e3), 2), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
+                "config": {"workload": cfg["workload"], "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
                            "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-4 (fused)", "launch": graph_note,
+                           "ddp": (f"bucket_cap_mb {args.bucket_mb}, static_graph, gradient_as_bucket_view, "
+                                   f"{'bf16' if args.grad_bf16 else 'fp32'} gradient all-reduce") if ddp else None,
                            "scan_io": "fp32 (as the reference calls it), fp32 state",
                            "l2": "per-step activations (> 10 GB) exceed the 126 MB L2; no explicit flush"},
                 "e2e": {"value": round(total / (ms_e2e / 1e3), 2), "unit": UNIT,
                         "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4,
                         "input_pipeline": "pinned host batch -> device staging buffer on a copy stream, one step ahead (double buffered)",
                         "ms_per_step": round(ms_e2e / args.steps, 3), "last_loss": round(last, 4)},
-                "gpu_launches": launches, "roofline": roof, "scan_fwd_bwd": allscan, "clocks": clocks}
+                "gpu_launches": launches, "roofline": roof,
+                ("scan_fwd_bwd" if args.model == "medmamba_t" else "ssd_fwd_bwd"): allscan, "clocks": clocks}
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line), flush=True)
@@ -458,9 +519,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 64)")
-    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-batch", type=int, default=REF_BATCH, help="batch of the CPU arm / cpu_baseline sample (BASELINE.json configs[0]: 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--model", default="medmamba_t", choices=sorted(MODELS), help="medmamba_t = BASELINE.json configs[1] (default), medssd = configs[2]")
+    ap.add_argument("--bucket-mb", type=int, default=8, help="DDP bucket size (N > 1)")
+    ap.add_argument("--grad-bf16", action="store_true", help="bf16-compressed gradient all-reduce (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

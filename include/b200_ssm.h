@@ -30,7 +30,7 @@ typedef void* b200_stream_t; /* cudaStream_t */
 
 typedef enum { B200_F32 = 0, B200_BF16 = 1, B200_F16 = 2 } b200_dtype;
 
-#define B200_SSCAN_MAX_DSTATE 256 /* selective_scan_common.h:11 (MAX_DSTATE) */
+#define B200_SSCAN_MAX_DSTATE 16 /* this build; the reference allows 256 (selective_scan_common.h:11, MAX_DSTATE) but every model uses 16 */
 #define B200_SSCAN_ROWS_PER_TASK 16
 
 /* ------------------------------------------------------------------------------------------
@@ -124,6 +124,10 @@ size_t b200_sscan_ckpt_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t
                              int32_t n_groups, int32_t ckpt_every);
 int b200_sscan_fwd(const b200_sscan_fwd_params* p, b200_stream_t stream);
 int b200_sscan_bwd(const b200_sscan_bwd_params* p, b200_stream_t stream);
+/* Which kernel generation the calling thread's last b200_sscan_fwd / _bwd launched: 2 = the TMA-staged kernels of sscan2.cu
+ * (fp32 tensors whose layouts tensor maps can describe: L % 4 == 0, 16-byte aligned bases and strides), 1 = sscan.cu (every other
+ * layout, 16-bit I/O, the z gate in the backward).  Both generations share the checkpoint format; for profilers and tests. */
+int b200_sscan_last_variant(void);
 
 /* ------------------------------------------------------------------------------------------
  * Strided twins of the cross-scan pack for the fused SS2D core (medical_image_classification_b200/cross.py::SS2DCoreFn;

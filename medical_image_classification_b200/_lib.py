@@ -75,7 +75,7 @@ _DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 # every symbol include/b200_ssm.h declares
 EXPORTS = [
-    "b200_sscan_ckpt_bytes", "b200_sscan_fwd", "b200_sscan_bwd",
+    "b200_sscan_ckpt_bytes", "b200_sscan_fwd", "b200_sscan_bwd", "b200_sscan_last_variant",
     "b200_cross_scan_pack", "b200_cross_scan_pack_bwd", "b200_cross_merge", "b200_cross_merge_bwd",
     "b200_cross_scan4", "b200_cross_scan4_bwd", "b200_ssd_merge4", "b200_ssd_merge4_bwd",
     "b200_ssd_workspace_bytes", "b200_ssd_bwd_scratch_bytes", "b200_ssd_fwd", "b200_ssd_bwd",

@@ -1089,6 +1089,9 @@ bool try_bwd(const b200_sscan_bwd_params* q, cudaStream_t st, int* rc);
 
 using namespace b200;
 
+static thread_local int g_last_variant = 0;
+extern "C" int b200_sscan_last_variant(void) { return g_last_variant; }
+
 extern "C" size_t b200_sscan_ckpt_bytes(int32_t batch, int32_t dim, int32_t seqlen, int32_t dstate, int32_t n_groups,
                                         int32_t ckpt_every) {
     (void)dstate;
@@ -1107,8 +1110,12 @@ extern "C" int b200_sscan_fwd(const b200_sscan_fwd_params* p, b200_stream_t stre
     cudaStream_t st = (cudaStream_t)stream;
     {
         int rc = 0;
-        if (v2::try_fwd(p, st, &rc)) return rc;
+        if (v2::try_fwd(p, st, &rc)) {
+            g_last_variant = 2;
+            return rc;
+        }
     }
+    g_last_variant = 1;
     switch (p->io_dtype) {
         case B200_F32: return launch_fwd<float>(p, st);
         case B200_BF16: return launch_fwd<__nv_bfloat16>(p, st);
@@ -1131,8 +1138,12 @@ extern "C" int b200_sscan_bwd(const b200_sscan_bwd_params* q, b200_stream_t stre
     cudaStream_t st = (cudaStream_t)stream;
     {
         int rc = 0;
-        if (v2::try_bwd(q, st, &rc)) return rc;
+        if (v2::try_bwd(q, st, &rc)) {
+            g_last_variant = 2;
+            return rc;
+        }
     }
+    g_last_variant = 1;
     switch (q->f.io_dtype) {
         case B200_F32: return launch_bwd<float>(q, st);
         case B200_BF16: return launch_bwd<__nv_bfloat16>(q, st);

@@ -33,6 +33,15 @@ from . import _lib
 _precision = 0
 _explicit = False
 
+# Optional per-call profiler (bench.py --model medssd): an object with begin() -> token and end(token, kind, shape), called
+# immediately around the C-ABI call on the current stream; shape = (batch, L, H, P, G, N, chunk, precision).
+_profiler = None
+
+
+def set_profiler(p) -> None:
+    global _profiler
+    _profiler = p
+
 
 def _effective_precision() -> int:
     if not _explicit and torch.is_autocast_enabled():
@@ -74,7 +83,7 @@ def _f32c(t):
 class SsdChunkScanFn(torch.autograd.Function):
     @staticmethod
     @_no_autocast
-    def forward(ctx, x, dt, A, B, C, D, dt_bias, initial_states, chunk_size, dt_softplus, dt_limit, return_final_states):
+    def forward(ctx, x, dt, A, B, C, D, dt_bias, initial_states, chunk_size, dt_softplus, dt_limit, return_final_states, prec):
         lib = _lib.load()
         batch, L, H, P = x.shape
         G, N = B.shape[2], B.shape[3]
@@ -86,12 +95,15 @@ class SsdChunkScanFn(torch.autograd.Function):
         nbytes = lib.b200_ssd_workspace_bytes(batch, L, H, P, G, N, chunk_size)
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
         p = _lib.SsdFwdParams()
-        prec = _effective_precision()
         _fill_fwd(p, x, dt_, A32, B_, C_, D32, bias32, chunk_size, dt_softplus, dt_limit, init32, prec)
         p.out_stride[:] = list(out.stride())
         p.out, p.final_states, p.workspace = out.data_ptr(), _lib.ptr(fin), ws.data_ptr()
+        prof = _profiler
         with torch.cuda.device(dev):
+            tok = prof.begin() if prof is not None else None
             _lib.check(lib.b200_ssd_fwd(ctypes.byref(p), _lib.stream_ptr(dev)), "b200_ssd_fwd")
+            if prof is not None:
+                prof.end(tok, "fwd", (batch, L, H, P, G, N, chunk_size, prec))
         ctx.save_for_backward(x, dt_, A32, B_, C_, D32, bias32, init32, out, ws)
         ctx.cfg = (chunk_size, bool(dt_softplus), tuple(dt_limit), prec)
         ctx.dtypes = (dt.dtype, A.dtype, B.dtype, C.dtype, None if D is None else D.dtype,
@@ -127,12 +139,16 @@ class SsdChunkScanFn(torch.autograd.Function):
         q.dout_stride[:] = list(dout.stride())
         q.dout, q.dx, q.ddt, q.dB, q.dC = dout.data_ptr(), dx.data_ptr(), ddt.data_ptr(), dB.data_ptr(), dC.data_ptr()
         q.dA, q.dD, q.ddt_bias, q.scratch = dA.data_ptr(), _lib.ptr(dD), _lib.ptr(dbias), scratch.data_ptr()
+        prof = _profiler
         with torch.cuda.device(dev):
+            tok = prof.begin() if prof is not None else None
             _lib.check(lib.b200_ssd_bwd(ctypes.byref(q), _lib.stream_ptr(dev)), "b200_ssd_bwd")
+            if prof is not None:
+                prof.end(tok, "bwd", (batch, L, H, P, G, N, chunk_size, precision))
         t_dt, t_A, t_B, t_C, t_D, t_bias = ctx.dtypes
         return (dx.to(x.dtype), ddt.to(t_dt), dA.to(t_A), dB.to(t_B), dC.to(t_C),
                 None if dD is None else dD.to(t_D), None if dbias is None else dbias.to(t_bias),
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bias=None, initial_states=None,
@@ -177,7 +193,8 @@ def mamba_chunk_scan_combined(x, dt, A, B, C, chunk_size, D=None, z=None, dt_bia
     if chunk_size % 32 != 0 or not 32 <= chunk_size <= 256:
         raise RuntimeError(f"mamba_chunk_scan_combined: chunk_size {chunk_size} must be a multiple of 32 in [32, 256]")
     res = SsdChunkScanFn.apply(x, dt, A, B, C, D_head, dt_bias, initial_states, chunk_size, dt_softplus,
-                               (float(dt_limit[0]), float(dt_limit[1])), return_final_states)
+                               (float(dt_limit[0]), float(dt_limit[1])), return_final_states,
+                               _effective_precision())   # read here: autocast is off inside the Function
     out, fin = res if return_final_states else (res, None)
     if D is not None and D_head is None:      # D with a head dimension: plain PyTorch on the side (unused by the models)
         out = out + x * D.to(x.dtype)

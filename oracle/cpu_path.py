@@ -21,8 +21,9 @@ import torch
 import torch.nn.functional as F
 
 import oracle
-from medical_image_classification_b200.models import PatchEmbed2D, PatchMerging2D, SS_Conv_SSM, channel_shuffle
+from medical_image_classification_b200.models import PatchEmbed2D, PatchMerging2D, SS_Conv_SSD, SS_Conv_SSM, channel_shuffle
 from medical_image_classification_b200.ss2d import SS2D
+from medical_image_classification_b200.ss2d_ssd import SS2D_with_SSD
 
 
 class OracleSelectiveScanFn(torch.autograd.Function):
@@ -109,7 +110,64 @@ class CpuPatchMerging2D(PatchMerging2D):
         return self.reduction(self.norm(x))
 
 
-_CPU_CLASS = {SS2D: CpuSS2D, SS_Conv_SSM: CpuSSConvSSM, PatchEmbed2D: CpuPatchEmbed2D, PatchMerging2D: CpuPatchMerging2D}
+class OracleSsdFn(torch.autograd.Function):
+    """mamba_chunk_scan_combined on CPU tensors through the from-definition fp64 recurrence (oracle/ssd_oracle.c)."""
+
+    @staticmethod
+    def forward(ctx, x, dt, A, B, C, D, dt_bias, dt_softplus):
+        out, _ = oracle.ssd_fwd(x, dt, A, B, C, D=D, dt_bias=dt_bias, dt_softplus=dt_softplus)
+        ctx.save_for_backward(x, dt, A, B, C, D, dt_bias)
+        ctx.softplus = dt_softplus
+        return torch.from_numpy(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, dt, A, B, C, D, dt_bias = ctx.saved_tensors
+        g = oracle.ssd_bwd(x, dt, A, B, C, D=D, dt_bias=dt_bias, dt_softplus=ctx.softplus, dout=dout.contiguous())
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a))
+        return t(g["dx"]), t(g["ddt"]), t(g["dA"]), t(g["dB"]), t(g["dC"]), t(g["dD"]), t(g["ddt_bias"]), None
+
+
+class CpuSS2DWithSSD(SS2D_with_SSD):
+    def forward(self, u, seqlen=None, seq_idx=None, cu_seqlens=None):      # SSD/MedSSD.py:310-402
+        B, H, W, C = u.shape
+        L, K = H * W, 4
+        zxbcdt = self.in_proj(u)
+        d_mlp = (zxbcdt.shape[-1] - 2 * self.d_ssm - 2 * self.ngroups * self.d_state - self.nheads) // 2
+        z0, x0, z, xBCdt = torch.split(
+            zxbcdt, [d_mlp, d_mlp, self.d_ssm, self.d_ssm + 2 * self.ngroups * self.d_state + self.nheads], dim=-1)
+        xBCdt = self.act(self.conv2d(xBCdt.permute(0, 3, 1, 2).contiguous()))
+        gn = self.ngroups * self.d_state
+        hwwh = torch.stack([xBCdt.reshape(B, -1, L), xBCdt.transpose(2, 3).reshape(B, -1, L)], dim=1)
+        xBCdts = torch.cat([hwwh, hwwh.flip(-1)], dim=1)
+        xs, Bs, Cs, dts = torch.split(xBCdts, [self.d_ssm, gn, gn, self.nheads], dim=2)
+        xs = xs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (-1, self.headdim))
+        Bs = Bs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (self.ngroups, -1))
+        Cs = Cs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (self.ngroups, -1))
+        dts = dts.float().reshape(B, -1, L).permute(0, 2, 1)
+        As = -torch.exp(self.A_logs.float())
+        y = OracleSsdFn.apply(xs.contiguous(), dts.contiguous(), As, Bs.contiguous(), Cs.contiguous(), self.Ds.float(),
+                              self.dt_bias.view(-1).float(), True)
+        y = y.reshape(B, L, K, -1)
+        inv_y = y[:, :, 2:4].flip(1)
+        wh_y = y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
+        invwh_y = inv_y[:, :, 1].view(B, W, H, -1).transpose(1, 2).reshape(B, L, -1)
+        out = (y[:, :, 0] + inv_y[:, :, 0] + wh_y + invwh_y).view(B, H, W, -1)
+        if self.rmsnorm:                                                    # gated RMSNorm, norm_before_gate=False, one group
+            v = out * F.silu(z)
+            out = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.norm.eps) * self.norm.weight
+        if d_mlp > 0:
+            out = torch.cat([F.silu(z0) * x0, out], dim=-1)
+        out = self.out_proj(out)
+        return self.dropout(out) if self.dropout is not None else out
+
+
+class CpuSSConvSSD(SS_Conv_SSD):
+    forward = CpuSSConvSSM.forward
+
+
+_CPU_CLASS = {SS2D: CpuSS2D, SS_Conv_SSM: CpuSSConvSSM, PatchEmbed2D: CpuPatchEmbed2D, PatchMerging2D: CpuPatchMerging2D,
+              SS2D_with_SSD: CpuSS2DWithSSD, SS_Conv_SSD: CpuSSConvSSD}
 
 
 def bind_cpu_core(model):
@@ -121,5 +179,5 @@ def bind_cpu_core(model):
         twin = _CPU_CLASS.get(type(mod))
         if twin is not None:
             mod.__class__ = twin
-            n += twin is CpuSS2D
+            n += twin in (CpuSS2D, CpuSS2DWithSSD)
     return n

@@ -19,6 +19,7 @@ def test_reference_arm_json_line():
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d, k
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["config"]["cpu_batch"] == 1          # --cpu-batch is honoured (round 1 picked the batch from a timing heuristic)
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and abs(cb["value"] - d["value"]) < 1e-6 * max(1.0, d["value"])
     e = d["e2e"]
@@ -33,3 +34,13 @@ def test_product_arm_needs_a_gpu():
                          text=True, timeout=600)
     assert out.returncode != 0                     # no silent CPU fallback
     assert not [l for l in out.stdout.splitlines() if l.startswith("{") and '"value"' in l]
+
+
+def test_reference_arm_medssd():
+    """BASELINE.json configs[2]: the same arm for the SSD family (eager CPU tree + the from-definition SSD oracle)."""
+    out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--model", "medssd", "--steps", "1", "--warmup", "0",
+                          "--cpu-batch", "1"], cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.strip().splitlines() if l.startswith("{")][0])
+    assert d["impl"] == "reference" and d["metric"] == "MedSSD train images/sec @224" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["config"]["cpu_batch"] == 1
