@@ -139,11 +139,12 @@ class ScanProfiler:
         self.enabled = False
 
     @staticmethod
-    def algorithmic_bytes(kind, u, delta, Bm):
+    def algorithmic_bytes(kind, u, delta, Bm, L=None):
         """s = bytes per I/O element, E = B*KD*L, Ebc = B*K*N*L.
         fwd: s*(3E + 2Ebc) + 4*(KD*N + 2KD);  bwd: s*(5E + 2Ebc) + 4*2Ebc + 4*(2KD*N + 4KD)."""
         s = u.element_size()
-        batch, KD, L = delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), delta.shape[-1]   # (B, KD, L) or a (B, K, D, L) view
+        batch, KD = delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1])   # (B, KD, L) or a (B, K, D, L) view
+        L = L or delta.shape[-1]                # the TRUE sequence length when rows are padded to a 16-byte pitch (49 -> 52)
         G, N = Bm.shape[1], Bm.shape[2]
         E, Ebc = batch * KD * L, batch * G * N * L
         if kind.startswith("fwd"):
@@ -160,14 +161,14 @@ class ScanProfiler:
         e0.record()
         return e0
 
-    def end(self, e0, kind, u, delta, Bm):
+    def end(self, e0, kind, u, delta, Bm, algo_len=None):
         if e0 is None:
             return
         e1 = self.torch.cuda.Event(enable_timing=True)
         e1.record()
         gen = "2" if self.lib.b200_sscan_last_variant() == 2 else ""
-        key = (kind + gen, (delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), delta.shape[-1]), Bm.shape[2], str(u.dtype))
-        self.records.append((key, self.algorithmic_bytes(kind, u, delta, Bm), e0, e1))
+        key = (kind + gen, (delta.shape[0], delta.numel() // (delta.shape[0] * delta.shape[-1]), algo_len or delta.shape[-1]), Bm.shape[2], str(u.dtype))
+        self.records.append((key, self.algorithmic_bytes(kind, u, delta, Bm, algo_len), e0, e1))
 
     def summary(self, peak_gbs, peak_src, steps):
         """Per (kernel, shape): launches, mean ms between events recorded immediately around the
@@ -381,7 +382,7 @@ def run_cuda(args):
     net = build_model(args.model).to(dev)
     use_graph = not args.no_graph
     step = TrainStep(net, lr=1e-4, autocast=torch.bfloat16, ddp=ddp, local_rank=local_rank, graph=use_graph,
-                     bucket_cap_mb=args.bucket_mb, grad_bf16=args.grad_bf16)
+                     bucket_cap_mb=args.bucket_mb, grad_bf16=args.grad_bf16, broadcast_buffers=not args.no_broadcast_buffers)
     model = step.model
     B = args.batch
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
@@ -525,6 +526,7 @@ def main():
     ap.add_argument("--model", default="medmamba_t", choices=sorted(MODELS), help="medmamba_t = BASELINE.json configs[1] (default), medssd = configs[2]")
     ap.add_argument("--bucket-mb", type=int, default=8, help="DDP bucket size (N > 1)")
     ap.add_argument("--grad-bf16", action="store_true", help="bf16-compressed gradient all-reduce (N > 1)")
+    ap.add_argument("--no-broadcast-buffers", action="store_true", help="skip DDP's per-step BatchNorm-buffer broadcast (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

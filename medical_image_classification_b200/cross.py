@@ -195,19 +195,26 @@ class SS2DCoreFn(torch.autograd.Function):
         M = W_all.shape[1]
         assert W_all.shape == (4, M, D) and M == 2 * N + D
         dev = x.device
-        x2 = torch.empty((2, D, B, L), dtype=torch.float32, device=dev)
-        strides = (L, D * B * L, B * L)                               # (batch, layout, row) element strides of x2
+        # Rows are laid out with a pitch Lp = L rounded up to 4 elements, so that every row of x2 / big starts on a 16-byte
+        # boundary and the TMA-staged scan kernels (csrc/sscan2.cu) apply at L = 49 too (stage 3: 7 x 7).  The pad columns of x2
+        # are zero, hence delta = B = C = u = 0 there: a pad step leaves the (zero) state and every gradient untouched whichever
+        # direction meets it first, so the scan simply runs over Lp steps.
+        Lp = (L + 3) // 4 * 4
+        x2 = torch.empty((2, D, B, Lp), dtype=torch.float32, device=dev) if Lp == L else torch.zeros((2, D, B, Lp), dtype=torch.float32, device=dev)
+        strides = (Lp, D * B * Lp, B * Lp)                            # (batch, layout, row) element strides of x2
         with torch.cuda.device(dev):
             _lib.check(lib.b200_cross_scan_pack_strided(x.data_ptr(), x2.data_ptr(), *strides, B, D, H, W, _lib.stream_ptr(dev)),
                        "b200_cross_scan_pack_strided")
         Wm = W_all.detach().float().reshape(2, 2 * M, D).contiguous()
         with _Tf32(tf32):
-            big = torch.bmm(Wm, x2.view(2, D, B * L))                  # (2, 2M, B*L)
-        big4 = big.view(4, M, B, L).permute(2, 0, 1, 3)                # (B, 4, M, L) view
+            big = torch.bmm(Wm, x2.view(2, D, B * Lp))                 # (2, 2M, B*Lp)
+        big4 = big.view(4, M, B, Lp).permute(2, 0, 1, 3)               # (B, 4, M, Lp) view
         A32, D32, b32 = _f32c(A), _f32c(Ds), _f32c(delta_bias)
         need_grad = any(ctx.needs_input_grad)
         ys, _, ckpt = launch_fwd(x2.permute(2, 0, 1, 3), big4[:, :, 2 * N:], A32, big4[:, :, :N], big4[:, :, N:2 * N], D32, None, b32,
-                                 True, REV_MASK, 2, want_ckpt=need_grad)
+                                 True, REV_MASK, 2, want_ckpt=need_grad, algo_len=L)
+        if Lp != L:
+            ys = ys[:, :, :L].contiguous()
         y = torch.empty((B, L, D), dtype=torch.float32, device=dev)
         _plane_op("b200_cross_merge", ys, y, B, D, H, W)
         if need_grad:
@@ -222,27 +229,32 @@ class SS2DCoreFn(torch.autograd.Function):
         x2, big, Wm, A32, D32, b32, ckpt = ctx.saved_tensors
         B, D, H, W, M, N, tf32 = ctx.meta
         L = H * W
+        Lp = x2.shape[-1]
         lib = _lib.load()
         dev = dy.device
         dy = dy.contiguous().float()
         d2 = torch.empty((B, 2 * D, L), dtype=torch.float32, device=dev)
         _plane_op("b200_cross_merge_bwd", dy, d2, B, D, H, W)
-        big4 = big.view(4, M, B, L).permute(2, 0, 1, 3)
+        if Lp != L:
+            d2 = torch.nn.functional.pad(d2, (0, Lp - L))              # zero upstream gradient at the pad steps
+        big4 = big.view(4, M, B, Lp).permute(2, 0, 1, 3)
         g_big = torch.empty_like(big)
-        g4 = g_big.view(4, M, B, L).permute(2, 0, 1, 3)                # (B, 4, M, L) view, like big4
-        gflat = g_big.view(4, M * B * L)
+        g4 = g_big.view(4, M, B, Lp).permute(2, 0, 1, 3)               # (B, 4, M, Lp) view, like big4
+        gflat = g_big.view(4, M * B * Lp)
         for k in range(4):                                             # dB, dC are accumulated with atomics (ddelta is written):
-            gflat[k, :2 * N * B * L].zero_()                           # four contiguous fills instead of one strided one
+            gflat[k, :2 * N * B * Lp].zero_()                          # four contiguous fills instead of one strided one
         du, _, dA, _, _, dD, dbias, _ = launch_bwd(x2.permute(2, 0, 1, 3), big4[:, :, 2 * N:], A32, big4[:, :, :N], big4[:, :, N:2 * N],
                                                    D32, None, b32, True, ckpt, d2, REV_MASK, 2, 2, True, True,
-                                                   ddelta=g4[:, :, 2 * N:], dB=g4[:, :, :N], dC=g4[:, :, N:2 * N])
-        x2m = x2.view(2, D, B * L)
+                                                   ddelta=g4[:, :, 2 * N:], dB=g4[:, :, :N], dC=g4[:, :, N:2 * N], algo_len=L)
+        if Lp != L:
+            du = du[:, :, :L].contiguous()
+        x2m = x2.view(2, D, B * Lp)
         with _Tf32(tf32):
             dW = _weight_grad_splitk(g_big, x2m)                       # (2, 2M, D)
-            gx2 = torch.bmm(Wm.transpose(1, 2), g_big)                 # (2, D, B*L)
+            gx2 = torch.bmm(Wm.transpose(1, 2), g_big)                 # (2, D, B*Lp)
         dx = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.b200_cross_scan_unpack4(du.data_ptr(), gx2.data_ptr(), L, D * B * L, B * L, dx.data_ptr(), B, D, H, W,
+            _lib.check(lib.b200_cross_scan_unpack4(du.data_ptr(), gx2.data_ptr(), Lp, D * B * Lp, B * Lp, dx.data_ptr(), B, D, H, W,
                                                    _lib.stream_ptr(dev)), "b200_cross_scan_unpack4")
         wdt, adt, ddt, bdt = ctx.dtypes
         return dx, dW.view(4, M, D).to(wdt), dA.to(adt), dD.to(ddt), dbias.to(bdt), None, None

@@ -28,7 +28,8 @@ from . import _lib
 CKPT_EVERY = 8  # steps between state checkpoints written by the forward for the recompute backward
 
 # Optional per-launch profiler (bench.py): an object with begin() -> token and
-# end(token, kind, u, delta, Bm), called immediately around the C-ABI launch on the current stream.
+# end(token, kind, u, delta, Bm, algo_len), called immediately around the C-ABI launch on the current stream; algo_len is the
+# caller's true sequence length when it runs the scan over rows padded to a 16-byte pitch (None otherwise).
 _profiler = None
 
 
@@ -97,7 +98,7 @@ def _check_inputs(u, delta, A, B, C, D, z, delta_bias, u_group_div):
 
 
 def launch_fwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, rev_mask=0, u_group_div=1,
-               want_ckpt=False, want_last_state=False):
+               want_ckpt=False, want_last_state=False, algo_len=None):
     """One b200_sscan_fwd call on prepared tensors (last stride 1, B/C 4-D, A/D/bias fp32 contiguous).
     Returns (out, last_state | None, ckpt | None)."""
     lib = _lib.load()
@@ -119,12 +120,12 @@ def launch_fwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, rev_mask=0
         tok = prof.begin() if prof is not None else None
         _lib.check(lib.b200_sscan_fwd(C.byref(p), _lib.stream_ptr(u.device)), "b200_sscan_fwd")
         if prof is not None:
-            prof.end(tok, "fwd", u, delta, Bm)
+            prof.end(tok, "fwd", u, delta, Bm, algo_len)
     return out, last_state, ckpt
 
 
 def launch_bwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, ckpt, dout, rev_mask=0,
-               u_group_div=1, dout_group_div=1, has_D=True, has_bias=True, ddelta=None, dB=None, dC=None):
+               u_group_div=1, dout_group_div=1, has_D=True, has_bias=True, ddelta=None, dB=None, dC=None, algo_len=None):
     """One b200_sscan_bwd call.  `dout` is (batch, dim / dout_group_div, L).
     Returns du (batch, dim, L), ddelta, dA, dB, dC (fp32), dD, ddelta_bias, dz.
     ddelta (batch, G, rows per group, L) and dB, dC (batch, G, N, L; fp32, ZERO-FILLED by the caller) may be passed as
@@ -165,7 +166,7 @@ def launch_bwd(u, delta, A32, Bm, Cm, D32, z, bias32, delta_softplus, ckpt, dout
         tok = prof.begin() if prof is not None else None
         _lib.check(lib.b200_sscan_bwd(C.byref(q), _lib.stream_ptr(dev)), "b200_sscan_bwd")
         if prof is not None:
-            prof.end(tok, "bwd", u, delta, Bm)
+            prof.end(tok, "bwd", u, delta, Bm, algo_len)
     return du, ddelta, dA, dB, dC, dD, dbias, dz
 
 

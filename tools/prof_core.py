@@ -12,7 +12,7 @@ class Hook:
     def __init__(self): self.rec = []
     def begin(self):
         e = torch.cuda.Event(enable_timing=True); e.record(); return e
-    def end(self, e0, kind, u, delta, Bm):
+    def end(self, e0, kind, u, delta, Bm, algo_len=None):
         e1 = torch.cuda.Event(enable_timing=True); e1.record(); self.rec.append((kind, e0, e1))
 
 
