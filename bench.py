@@ -44,6 +44,10 @@ MODELS = {
     "medssd": dict(metric="MedSSD train images/sec @224",
                    workload=("MedSSD (SSD/MedSSD.py VSSM depths 2-2-4-2, dims 128-1024, d_state 128 -> N' = 512, 6 classes) bf16-autocast "
                              "training step, batch 64 per GPU, synthetic 3x224x224 (BASELINE.json configs[2])")),
+    # BASELINE.json configs[3], first half: MedSSD_kan (the CrossMamba VFEFM fusion network of the second half is not mirrored)
+    "medssd_kan": dict(metric="MedSSD_kan train images/sec @224",
+                       workload=("MedSSD_kan (MedSSD_kan/MedSSD_kan.py VSSM depths 2-2-4-2, dims 128-1024, d_state 16 -> N' = 64, KAN head, "
+                                 "6 classes) bf16-autocast training step, synthetic 3x224x224 (BASELINE.json configs[3])")),
 }
 METRIC = MODELS["medmamba_t"]["metric"]
 WORKLOAD = MODELS["medmamba_t"]["workload"]

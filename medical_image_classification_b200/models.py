@@ -258,9 +258,31 @@ class VSSM(nn.Module):
         return self.head(x)
 
 
+class VSSM_KAN(VSSM):
+    """MedSSD_kan: the SSD backbone with the KAN classification head `kans` in place of `head`
+    (reference MedSSD_kan/MedSSD_kan.py:1097-1204; d_state 16 -> N' = 64)."""
+
+    def __init__(self, num_classes=1000, dims=(128, 256, 512, 1024), d_state=16, block=None, **kw):
+        from .kan_head import KansModule
+        super().__init__(num_classes=0, dims=dims, d_state=d_state, block=block or SS_Conv_SSD, **kw)
+        del self.head
+        self.num_classes = num_classes
+        self.kans = KansModule(in_channels=self.num_features, out_channels=num_classes)
+
+    def forward(self, x, update_grid=False):
+        x = self.forward_backbone(x)
+        x = self.avgpool(x.permute(0, 3, 1, 2)).flatten(1)
+        return self.kans(x.float())
+
+
 def medmamba_t(num_classes=6, **kw):
     """MedMamba-T, the configuration BASELINE.json names (depths 2-2-4-2, dims 96-768)."""
     return VSSM(num_classes=num_classes, depths=[2, 2, 4, 2], dims=[96, 192, 384, 768], **kw)
+
+
+def medssd_kan(num_classes=6, dims=(128, 256, 512, 1024), d_state=16, depths=(2, 2, 4, 2), **kw):
+    """MedSSD_kan (BASELINE.json configs[3]): MedSSD backbone, d_state 16, KAN head."""
+    return VSSM_KAN(num_classes=num_classes, depths=list(depths), dims=list(dims), d_state=d_state, **kw)
 
 
 def medssd(num_classes=6, dims=(128, 256, 512, 1024), d_state=128, depths=(2, 2, 4, 2), **kw):

@@ -299,10 +299,41 @@ def medmamba_real_dims_case(seed=0):
     print("wrote medmamba_real_dims: loss", float(loss), "logits_eval[0]", rec["logits_eval"][0])
 
 
+def kan_head_case(seed=0):
+    """Reference KansModule (MedSSD_kan/MedSSD_kan.py:475-501: two pykan-style KANLayers + BatchNorm1d) forward / backward with
+    its state_dict, for the host-side head mirror medical_image_classification_b200/kan_head.py (outside the hot path)."""
+    mod = ref_import.load_medssd("MedSSD_kan/MedSSD_kan.py", "ref_MedSSD_kan")
+    torch.manual_seed(seed)
+    m = mod.KansModule(24, 6)
+    with torch.no_grad():                                  # move every knot vector a little so the grids are not all identical
+        m.kan1.grid.add_(0.01 * torch.randn(24, 1))
+    x = (1.2 * torch.randn(10, 24)).requires_grad_()
+    g = torch.randn(10, 6)
+    rec = {"x": _np(x), "g": _np(g)}
+    for k, v in m.state_dict().items():
+        rec["sd." + k] = _np(v)
+    m.train()
+    out = m(x)
+    out.backward(g)
+    rec["out_train"] = _np(out)
+    rec["dx"] = _np(x.grad)
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            rec["grad." + k] = _np(p.grad)
+    m.eval()
+    with torch.no_grad():
+        rec["out_eval"] = _np(m(x))
+    np.savez_compressed(os.path.join(OUT, "kan_head.npz"), **rec)
+    print("wrote kan_head")
+
+
 def main():
     assert ref_import.available(), "/root/reference is not mounted"
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--kan-only" in sys.argv:
+        kan_head_case()
+        return
     if "--real-dims-only" in sys.argv:
         medmamba_real_dims_case()
         return
@@ -337,6 +368,7 @@ def main():
     ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
     medssd_case()
     medmamba_real_dims_case()
+    kan_head_case()
     crossmamba_case("d32_6x5", 32, 8, 16, 6, 5, 2)
     atrous_case("8x8", 2, 3, 8, 8)
     atrous_case("7x9", 1, 5, 7, 9, seed=1)

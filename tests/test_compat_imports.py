@@ -112,3 +112,14 @@ def test_crossmamba_imports_and_matches_mirror(compat_path):
     m = CrossMamba(d_model=32, d_state=16, headdim=16)
     assert _shapes(r) == _shapes(m)
     m.load_state_dict(r.state_dict(), strict=True)
+
+
+def test_medssd_kan_imports_and_matches_mirror(compat_path):
+    """BASELINE.json configs[3]: MedSSD_kan (SSD backbone, d_state 16, pykan-style head) through the compat package."""
+    ref = _load("MedSSD_kan/MedSSD_kan.py")
+    from medical_image_classification_b200.models import medssd_kan
+    torch.manual_seed(0)
+    r = ref.VSSM(num_classes=6, depths=[1, 1, 1, 1], dims=[64, 128, 256, 512], d_state=16)
+    m = medssd_kan(num_classes=6, depths=(1, 1, 1, 1), dims=(64, 128, 256, 512), d_state=16)
+    assert _shapes(r) == _shapes(m)
+    m.load_state_dict(r.state_dict(), strict=True)
