@@ -181,14 +181,22 @@ sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_
 #pragma unroll
             for (int st = 0; st < TC; ++st) {
                 const float2 dd = make_float2(dl[st], dl[st]), qq = make_float2(q[st], q[st]);
+#ifdef B200_DBG_NO_BC
+                const float4 b0 = make_float4(dl[st], q[st], dl[st], q[st]), b1 = b0, c0 = b0, c1 = b0;
+#else
                 const float4 b0 = *reinterpret_cast<const float4*>(tB + st * TBP), b1 = *reinterpret_cast<const float4*>(tB + st * TBP + 4);
                 const float4 c0 = *reinterpret_cast<const float4*>(tC + st * TBP), c1 = *reinterpret_cast<const float4*>(tC + st * TBP + 4);
+#endif
                 const float2 B2[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
                 const float2 C2[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
                 float2 y2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
+#ifdef B200_DBG_NO_EX2
+                    const float2 a = __fmul2_rn(dd, A2[qd]);
+#else
                     const float2 a = ex2_2(__fmul2_rn(dd, A2[qd]));
+#endif
                     x[qd] = __ffma2_rn(a, x[qd], __fmul2_rn(qq, B2[qd]));
                     y2 = __ffma2_rn(C2[qd], x[qd], y2);
                 }
@@ -312,6 +320,11 @@ struct BwdChunkCtx {
 // MODE says what happens to the row-pair sums vB / vC of every step (the select-free rounds of the channel reduction):
 //   0: park = partner(i ^ 4)'s sums        1: park = partner(i ^ 2)'s (sums + park)
 //   2: park += partner(i ^ 4)'s sums       3: park += sums
+#ifdef B200_DBG_NO_SHFL
+#define BWD_SHFL_XOR(v, m) (v)
+#else
+#define BWD_SHFL_XOR(v, m) __shfl_xor_sync(0xffffffffu, (v), (m))
+#endif
 template <int MODE>
 __device__ __forceinline__ void bwd_state(BwdChunkCtx& cx, const float* bB, const float* bC, const int off, const float2 A2j, const float2 xm1,
                                           float2& hj, float2& dAj, float (&park)[2 * TC]) {
@@ -327,7 +340,11 @@ __device__ __forceinline__ void bwd_state(BwdChunkCtx& cx, const float* bB, cons
         float2 xs = xm1;
 #pragma unroll
         for (int s = 0; s < TC; ++s) {
+#ifdef B200_DBG_NO_EX2
+            a[s] = __fmul2_rn(cx.dl2[s], A2j);
+#else
             a[s] = ex2_2(__fmul2_rn(cx.dl2[s], A2j));
+#endif
             xs = __ffma2_rn(a[s], xs, __fmul2_rn(cx.q2[s], make_float2(Bv[s], Bv[s])));
             x[s] = xs;
         }
@@ -343,14 +360,14 @@ __device__ __forceinline__ void bwd_state(BwdChunkCtx& cx, const float* bB, cons
         const float2 xprev = s > 0 ? x[s - 1] : xm1;
         const float2 g = __ffma2_rn(cx.go2[s], make_float2(Cv[s], Cv[s]), gn);
         if (MODE == 0) {
-            park[TC + s] = __shfl_xor_sync(0xffffffffu, fmaf(cx.go2[s].y, x[s].y, cx.go2[s].x * x[s].x), 4);   // summed over the row pair
-            park[s] = __shfl_xor_sync(0xffffffffu, fmaf(g.y, cx.q2[s].y, g.x * cx.q2[s].x), 4);
+            park[TC + s] = BWD_SHFL_XOR(fmaf(cx.go2[s].y, x[s].y, cx.go2[s].x * x[s].x), 4);   // summed over the row pair
+            park[s] = BWD_SHFL_XOR(fmaf(g.y, cx.q2[s].y, g.x * cx.q2[s].x), 4);
         } else if (MODE == 1) {
-            park[TC + s] = __shfl_xor_sync(0xffffffffu, fmaf(cx.go2[s].y, x[s].y, fmaf(cx.go2[s].x, x[s].x, park[TC + s])), 2);
-            park[s] = __shfl_xor_sync(0xffffffffu, fmaf(g.y, cx.q2[s].y, fmaf(g.x, cx.q2[s].x, park[s])), 2);
+            park[TC + s] = BWD_SHFL_XOR(fmaf(cx.go2[s].y, x[s].y, fmaf(cx.go2[s].x, x[s].x, park[TC + s])), 2);
+            park[s] = BWD_SHFL_XOR(fmaf(g.y, cx.q2[s].y, fmaf(g.x, cx.q2[s].x, park[s])), 2);
         } else if (MODE == 2) {
-            park[TC + s] += __shfl_xor_sync(0xffffffffu, fmaf(cx.go2[s].y, x[s].y, cx.go2[s].x * x[s].x), 4);
-            park[s] += __shfl_xor_sync(0xffffffffu, fmaf(g.y, cx.q2[s].y, g.x * cx.q2[s].x), 4);
+            park[TC + s] += BWD_SHFL_XOR(fmaf(cx.go2[s].y, x[s].y, cx.go2[s].x * x[s].x), 4);
+            park[s] += BWD_SHFL_XOR(fmaf(g.y, cx.q2[s].y, g.x * cx.q2[s].x), 4);
         } else {
             park[TC + s] = fmaf(cx.go2[s].y, x[s].y, fmaf(cx.go2[s].x, x[s].x, park[TC + s]));
             park[s] = fmaf(g.y, cx.q2[s].y, fmaf(g.x, cx.q2[s].x, park[s]));
