@@ -386,7 +386,7 @@ def run_cuda(args):
     net = build_model(args.model).to(dev)
     use_graph = not args.no_graph
     step = TrainStep(net, lr=1e-4, autocast=torch.bfloat16, ddp=ddp, local_rank=local_rank, graph=use_graph,
-                     bucket_cap_mb=args.bucket_mb, grad_bf16=args.grad_bf16, broadcast_buffers=not args.no_broadcast_buffers)
+                     bucket_cap_mb=args.bucket_mb, grad_bf16=args.grad_bf16, broadcast_buffers=args.broadcast_buffers)
     model = step.model
     B = args.batch
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
@@ -491,7 +491,7 @@ def run_cuda(args):
                 "data": "synthetic",
                 "config": {"workload": cfg["workload"], "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
                            "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-4 (fused)", "launch": graph_note,
-                           "ddp": (f"bucket_cap_mb {args.bucket_mb}, static_graph, gradient_as_bucket_view, "
+                           "ddp": (f"bucket_cap_mb {args.bucket_mb}, static_graph, gradient_as_bucket_view, broadcast_buffers={args.broadcast_buffers}, "
                                    f"{'bf16' if args.grad_bf16 else 'fp32'} gradient all-reduce") if ddp else None,
                            "scan_io": "fp32 (as the reference calls it), fp32 state",
                            "l2": "per-step activations (> 10 GB) exceed the 126 MB L2; no explicit flush"},
@@ -530,7 +530,8 @@ def main():
     ap.add_argument("--model", default="medmamba_t", choices=sorted(MODELS), help="medmamba_t = BASELINE.json configs[1] (default), medssd = configs[2]")
     ap.add_argument("--bucket-mb", type=int, default=8, help="DDP bucket size (N > 1)")
     ap.add_argument("--grad-bf16", action="store_true", help="bf16-compressed gradient all-reduce (N > 1)")
-    ap.add_argument("--no-broadcast-buffers", action="store_true", help="skip DDP's per-step BatchNorm-buffer broadcast (N > 1)")
+    ap.add_argument("--broadcast-buffers", action="store_true",
+                    help="re-enable DDP's per-step broadcast of rank 0's BatchNorm statistics (N > 1; see train_step.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -16,6 +16,12 @@ What is B200-specific here:
     buckets (`bucket_cap_mb`, default 8 MB instead of PyTorch's 25) so that the LAST bucket -- stage-0 / patch-embed
     gradients, ready only when backward ends -- leaves a short exposed all-reduce tail, `gradient_as_bucket_view=True`
     (no gradient copy into the buckets), `static_graph=True`;
+  * `broadcast_buffers=False`: DDP's default re-broadcasts rank 0's BatchNorm running statistics before every forward
+    (`ddp_train.py:134` keeps that default).  In training mode BatchNorm normalises with batch statistics, so the broadcast never
+    changes a gradient or a weight, and rank 0 is never
+    overwritten: the validation accuracy it logs and the checkpoint it saves (`ddp_train.py:181-193`, main process only) are bit-identical either way.  Skipping it removes ~90 small broadcasts (one coalesced launch plus
+    its dependencies) from every step: 24.64 -> 24.43 ms at N = 2 (`profiles/bench_r02_n2*.json`).  Pass True to get DDP's default
+    back (ranks > 0 then evaluate with rank 0's statistics);
   * optional bf16 gradient compression of the all-reduce payload (`grad_bf16=True`: PyTorch's bf16_compress_hook);
     off by default because the reference reduces fp32 gradients.
 """
@@ -27,7 +33,7 @@ import torch.distributed as dist
 
 class TrainStep:
     def __init__(self, net, lr=1e-4, autocast=torch.bfloat16, ddp=False, local_rank=0, graph=True, bucket_cap_mb=8,
-                 grad_bf16=False, broadcast_buffers=True, loss_fn=None):
+                 grad_bf16=False, broadcast_buffers=False, loss_fn=None):
         self.net = net
         self.dev = next(net.parameters()).device
         if self.dev.type != "cuda":
