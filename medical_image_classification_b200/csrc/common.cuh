@@ -29,6 +29,13 @@ cudaError_t func_attr_per_device(const void* kernel, cudaFuncAttribute attr, int
         }                                \
     } while (0)
 
+// ---- checkpoint record layout (shared by both kernel generations) ----------------------------------------------------
+// One record = the 16 x 16 state entering a chunk = 256 floats: word  ckpt_state_pos(n) + 2 * (row & 7) + (row >> 3).
+// States are grouped in quads of 64 words; inside ODD quads the 16-word blocks of states (0,1) and (2,3) are swapped, so a
+// record copied verbatim into shared memory (one 1 KB bulk copy) is read without bank conflicts by the backward's
+// [state quad][row pair] lanes (a half-warp = two quads x 8 row pairs x 8 bytes covers all 32 banks).
+__host__ __device__ constexpr int ckpt_state_pos(int n) { return (n >> 2) * 64 + ((((n & 3) ^ ((n >> 2) & 1))) << 4); }
+
 // ---- dtype helpers ---------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }

@@ -246,13 +246,13 @@ __device__ __forceinline__ void fill_bc_sync(float* tile, const T* base, int64_t
     }
 }
 
-// One chunk of checkpoints (256 floats, [n][row pair][2]) -> padded tile.
+// One chunk of checkpoints (256 floats, record layout: ckpt_state_pos in common.cuh) -> padded tile [n][row pair][2].
 __device__ __forceinline__ void stage_ckpt(float* tile, const float* src, int lane) {
 #pragma unroll
     for (int k0 = 0; k0 < NS * TR / 4; k0 += 32) {
         const int k = k0 + lane;
         const int n = k >> 2, part = k & 3;
-        cp_async16(tile + (n >> 2) * CKS + (n & 3) * 16 + part * 4, src + k * 4, true);
+        cp_async16(tile + (n >> 2) * CKS + (n & 3) * 16 + part * 4, src + ckpt_state_pos(n) + part * 4, true);
     }
 }
 
@@ -512,7 +512,7 @@ __device__ __forceinline__ void sscan_fwd_body(const b200_sscan_fwd_params& p, c
 #pragma unroll
         for (int j = 0; j < SPT; ++j) {
             const int n = sq * SPT + j;
-            if (ck != nullptr && c > 0) *reinterpret_cast<float2*>(ck + (size_t)(c - 1) * NS * TR + n * TR + 2 * i) = x[j];
+            if (ck != nullptr && c > 0) *reinterpret_cast<float2*>(ck + (size_t)(c - 1) * NS * TR + ckpt_state_pos(n) + 2 * i) = x[j];
             float Bv[TC], Cv[TC];
             load8_steps(&sm.bc[buf][0][sq * BCS + j * TC], rev, Bv);
             load8_steps(&sm.bc[buf][1][sq * BCS + j * TC], rev, Cv);

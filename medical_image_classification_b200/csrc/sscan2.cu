@@ -49,11 +49,13 @@ struct __align__(1024) FwdSmem {
 
 __device__ __forceinline__ float2 ex2_2(float2 e) { return make_float2(ex2(e.x), ex2(e.y)); }
 
-template <bool HAS_Z>
+template <bool HAS_Z, bool SOFTPLUS>
 __global__ void __launch_bounds__(32, 11)
 sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_constant__ FwdMaps tm, const unsigned tx_bytes,
                   const int zero_fill) {
     __shared__ FwdSmem sm;
+    const unsigned sbase = smem_addr(&sm);   // one generic -> shared conversion for everything the TMA engine touches
+    constexpr unsigned OFF_BAR = (unsigned)offsetof(FwdSmem, bar), STAGE_BYTES = 4u * TR * WIN * 4u, TILE_BYTES = (unsigned)TR * WIN * 4u;
     const int lane = threadIdx.x;
     const int r = lane & 15, h = lane >> 4;
     const int L = p.seqlen, N = p.dstate;
@@ -75,20 +77,22 @@ sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_
     }
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.bar[s], 1);
+        for (int s = 0; s < NSTAGE; ++s) mbar_init_a(sbase + OFF_BAR + 8u * s, 1);
         mbar_init_fence();
     }
     __syncwarp();
-    auto issue = [&](int w) {   // lane 0: the four tiles of window w
-        const int s = w % NSTAGE;
+    const int gu = g / p.u_group_div;
+    auto issue = [&](int w) {   // one thread (elect_one): the four tiles of window w
+        const unsigned s = (unsigned)w % NSTAGE;
         const int l_lo = rev ? L - (w + 1) * WIN : w * WIN;
-        mbar_expect_tx(&sm.bar[s], tx_bytes);
-        tma_load_4d(sm.win[s][0], &tm.u, l_lo, r0, g / p.u_group_div, b, &sm.bar[s]);
-        tma_load_4d(sm.win[s][1], &tm.delta, l_lo, r0, g, b, &sm.bar[s]);
-        tma_load_4d(sm.win[s][2], &tm.B, l_lo, 0, g, b, &sm.bar[s]);
-        tma_load_4d(sm.win[s][3], &tm.C, l_lo, 0, g, b, &sm.bar[s]);
+        const unsigned bar = sbase + OFF_BAR + 8u * s, dst = sbase + s * STAGE_BYTES;   // win is the first member
+        mbar_expect_tx_a(bar, tx_bytes);
+        tma_load_4d_a(dst, &tm.u, l_lo, r0, gu, b, bar);
+        tma_load_4d_a(dst + TILE_BYTES, &tm.delta, l_lo, r0, g, b, bar);
+        tma_load_4d_a(dst + 2 * TILE_BYTES, &tm.B, l_lo, 0, g, b, bar);
+        tma_load_4d_a(dst + 3 * TILE_BYTES, &tm.C, l_lo, 0, g, b, bar);
     };
-    if (lane == 0) {
+    if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s)
             if (s < nwin) issue(s);
@@ -105,11 +109,10 @@ sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_
     }
     const float bias = (p.delta_bias && row_ok) ? __ldg(p.delta_bias + d) : 0.f;
     const float Dv = (p.D && row_ok) ? __ldg(p.D + d) : 0.f;
-    const bool softplus = p.delta_softplus != 0;
     float* o_row = (float*)p.out + (size_t)b * p.out_batch_stride + (size_t)d * p.out_row_stride;
     const float* z_row = HAS_Z ? (const float*)p.z + (size_t)b * p.z_batch_stride + (size_t)d * p.z_row_stride : nullptr;
-    // checkpoint record of a chunk: [state][row pair (r & 7)][r >> 3]
-    float* ck = p.ckpt ? p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR + (8 * h) * TR + 2 * (r & 7) + (r >> 3) : nullptr;
+    // checkpoint record of a chunk: word ckpt_state_pos(state) + 2 * (r & 7) + (r >> 3)  (common.cuh)
+    float* ck = p.ckpt ? p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR + 128 * h + 2 * (r & 7) + (r >> 3) : nullptr;
 
     const int rsw = r & 7;                       // swizzle key of this lane's row
     const int tn = lane >> 1, tpart = lane & 1;  // B / C transposition: state, 4-step half
@@ -121,7 +124,7 @@ sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_
 
     for (int w = 0; w < nwin; ++w) {
         const int s = w % NSTAGE;
-        mbar_wait(&sm.bar[s], (w / NSTAGE) & 1);
+        mbar_wait_a(sbase + OFF_BAR + 8u * (unsigned)s, (w / NSTAGE) & 1);
         const float* wu = sm.win[s][0] + r * WIN;
         const float* wd = sm.win[s][1] + r * WIN;
         const float* wB = sm.win[s][2] + tn * WIN;
@@ -148,7 +151,7 @@ sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 float a = odl[e] + bias;
-                if (softplus) a = softplus_sigmoid(a).sp;
+                if (SOFTPLUS) a = softplus_sigmoid(a).sp;
                 odl[e] = ok4 ? a : 0.f;
                 oq[e] = odl[e] * ou[e];
             }
@@ -169,9 +172,9 @@ sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_
             if (ck != nullptr && c > 0) {
                 float* cc = ck + (size_t)(c - 1) * NS * TR;
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                    __stcs(cc + (2 * qd) * TR, x[qd].x);
-                    __stcs(cc + (2 * qd + 1) * TR, x[qd].y);
+                for (int qd = 0; qd < 4; ++qd) {   // state 8 h + 2 qd (+ 1); the 128 h term is in ck
+                    __stcs(cc + ckpt_state_pos(2 * qd), x[qd].x);
+                    __stcs(cc + ckpt_state_pos(2 * qd + 1), x[qd].y);
                 }
             }
             // ---- recurrence: 8 steps x 4 state pairs ----
@@ -224,7 +227,7 @@ sscan_fwd2_kernel(const __grid_constant__ b200_sscan_fwd_params p, const __grid_
             }
         }
         __syncwarp();   // every lane is done with this window's tiles
-        if (lane == 0 && w + NSTAGE < nwin) {
+        if (w + NSTAGE < nwin && elect_one()) {
             fence_proxy_async();
             issue(w + NSTAGE);
         }
@@ -263,7 +266,6 @@ constexpr int CPWB = WB / TC;      // chunks per window
 constexpr int NSTB = 2;            // ring stages: a stage is refilled once its window's stores have left it
 constexpr int EXS = 24;            // exchange tiles: words per scan step (16 used; 24 keeps the STS.64 conflict free)
 constexpr int RDS = 144;           // state-reduction tile: words per state quad
-constexpr int CKP = 4 * TR + 16;      // checkpoint tile: words per state quad (64 + 16: the two quads of a half-warp hit disjoint banks)
 constexpr float kLn2 = 0.6931471805599453f;
 #ifndef B200_BWD_REGS
 #define B200_BWD_REGS 168   // 3 warps per SM sub-partition (16 K registers each): 12 per SM, one wave at the stage-0 shape
@@ -290,7 +292,7 @@ struct __align__(1024) BwdSmem {
     float exd[TC * EXS];                // delta'
     float exg[TC * EXS];                // dout
     float2 priv[PRIV_SLOTS][4][32];     // per-lane accumulators that do not fit in registers: running dA (and the adjoint carry)
-    float ck[2][4 * CKP];               // [chunk parity] state entering the chunk: [state quad (pitch CKP)][state][row pair][2]
+    float ck[2][NS * TR];               // [chunk parity] state entering the chunk: the 1 KB record as stored (ckpt_state_pos, common.cuh)
     uint64_t bar[NSTB];
     uint64_t ckbar[2];
 };
@@ -399,10 +401,16 @@ __device__ __forceinline__ void bwd_slot(BwdChunkCtx& cx, const float* pB, const
     }
 }
 
+template <bool SOFTPLUS>
 __global__ void __maxnreg__(B200_BWD_REGS)
 sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_constant__ BwdMaps tm, const unsigned tx_bytes,
                   const int zero_fill) {
     __shared__ BwdSmem sm;
+    // shared-memory addresses of everything the bulk-copy engine touches, from ONE generic -> shared conversion
+    const unsigned sbase = smem_addr(&sm);
+    constexpr unsigned OFF_WIN = (unsigned)offsetof(BwdSmem, win), OFF_CK = (unsigned)offsetof(BwdSmem, ck);
+    constexpr unsigned OFF_BAR = (unsigned)offsetof(BwdSmem, bar), OFF_CKBAR = (unsigned)offsetof(BwdSmem, ckbar);
+    constexpr unsigned STAGE_BYTES = 5u * TR * WB * 4u, TILE_BYTES = (unsigned)TR * WB * 4u;
     const b200_sscan_fwd_params& p = q.f;
     const int lane = threadIdx.x;
     const int sq = lane >> 3, i = lane & 7;
@@ -426,9 +434,9 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
     }
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTB; ++s) mbar_init(&sm.bar[s], 1);
-        mbar_init(&sm.ckbar[0], 1);
-        mbar_init(&sm.ckbar[1], 1);
+        for (int s = 0; s < NSTB; ++s) mbar_init_a(sbase + OFF_BAR + 8u * s, 1);
+        mbar_init_a(sbase + OFF_CKBAR, 1);
+        mbar_init_a(sbase + OFF_CKBAR + 8u, 1);
         mbar_init_fence();
     }
     __syncwarp();
@@ -437,17 +445,18 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
         const int wv = nwin - 1 - v;
         return rev ? L - (wv + 1) * WB : wv * WB;
     };
-    auto issue = [&](int v) {
-        const int s = v % NSTB;
+    auto issue = [&](int v) {   // one thread (elect_one): the five tiles of the v-th window visited
+        const unsigned s = (unsigned)v % NSTB;
         const int l_lo = win_lo(v);
-        mbar_expect_tx(&sm.bar[s], tx_bytes);
-        tma_load_4d(sm.win[s][0], &tm.u, l_lo, r0, gu, b, &sm.bar[s]);
-        tma_load_4d(sm.win[s][1], &tm.delta, l_lo, r0, g, b, &sm.bar[s]);
-        tma_load_4d(sm.win[s][2], &tm.dout, l_lo, r0, gd, b, &sm.bar[s]);
-        tma_load_4d(sm.win[s][3], &tm.B, l_lo, 0, g, b, &sm.bar[s]);
-        tma_load_4d(sm.win[s][4], &tm.C, l_lo, 0, g, b, &sm.bar[s]);
+        const unsigned bar = sbase + OFF_BAR + 8u * s, w = sbase + OFF_WIN + s * STAGE_BYTES;
+        mbar_expect_tx_a(bar, tx_bytes);
+        tma_load_4d_a(w, &tm.u, l_lo, r0, gu, b, bar);
+        tma_load_4d_a(w + TILE_BYTES, &tm.delta, l_lo, r0, g, b, bar);
+        tma_load_4d_a(w + 2 * TILE_BYTES, &tm.dout, l_lo, r0, gd, b, bar);
+        tma_load_4d_a(w + 3 * TILE_BYTES, &tm.B, l_lo, 0, g, b, bar);
+        tma_load_4d_a(w + 4 * TILE_BYTES, &tm.C, l_lo, 0, g, b, bar);
     };
-    if (lane == 0) {
+    if (elect_one()) {
         issue(0);
         if (nwin > 1) issue(1);
     }
@@ -468,18 +477,16 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
     const float biasB = (p.delta_bias && okB) ? __ldg(p.delta_bias + chB) : 0.f;
     const float DA = (p.D && okA) ? __ldg(p.D + chA) : 0.f;
     const float DB = (p.D && okB) ? __ldg(p.D + chB) : 0.f;
-    const bool softplus = p.delta_softplus != 0;
     float dD_A = 0.f, dD_B = 0.f, dbias_A = 0.f, dbias_B = 0.f;
     const float* ck = p.ckpt + (size_t)task * (size_t)(nck - 1) * NS * TR;
-    // checkpoint of the state entering chunk c (c >= 1): 1 KB record -> tile ck[c & 1], one 256-byte bulk copy per state quad
-    auto issue_ck = [&](int c) {
-        const float* src = ck + (size_t)(c - 1) * NS * TR;
-        uint64_t* bar = &sm.ckbar[c & 1];
-        mbar_expect_tx(bar, NS * TR * 4);
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) bulk_load_1d(&sm.ck[c & 1][qd * CKP], src + qd * 4 * TR, 4 * TR * 4, bar);
+    // checkpoint of the state entering chunk c (c >= 1): the 1 KB record -> tile ck[c & 1], ONE bulk copy (the record layout is
+    // already the conflict-free shared-memory layout)
+    auto issue_ck = [&](int c) {   // one thread (elect_one)
+        const unsigned bar = sbase + OFF_CKBAR + 8u * (c & 1);
+        mbar_expect_tx_a(bar, NS * TR * 4);
+        bulk_load_1d_a(sbase + OFF_CK + (unsigned)(c & 1) * (NS * TR * 4), ck + (size_t)(c - 1) * NS * TR, NS * TR * 4, bar);
     };
-    if (lane == 0 && nck > 1) issue_ck(nck - 1);
+    if (nck > 1 && elect_one()) issue_ck(nck - 1);
     int ck_uses = 0;   // completed waits on the checkpoint barriers (chunks are visited in descending order: parity alternates)
 
     const int c0 = 2 * sq;                                           // this lane's two memory columns of every chunk
@@ -488,10 +495,11 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
     const int tn = lane >> 1, tpart = lane & 1;                      // reversed B / C copy: state, 4-step half
     const int b0 = i & 1;
 
+    int refill = -1;   // window whose loads wait for the stage's stores to have left (issued one chunk into the next window)
     for (int v = 0; v < nwin; ++v) {
         const int wv = nwin - 1 - v;
         const int s = v % NSTB;
-        mbar_wait(&sm.bar[s], (v / NSTB) & 1);
+        mbar_wait_a(sbase + OFF_BAR + 8u * (unsigned)s, (v / NSTB) & 1);
         float* wu = sm.win[s][0];
         float* wd = sm.win[s][1];
         const float* wg = sm.win[s][2];
@@ -504,11 +512,13 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
             const int la = (rev ? L - (c + 1) * TC : c * TC) + c0;
             const bool v01 = (unsigned)la < (unsigned)L; // L % 4 == 0 and c0 even: both columns in or both out
             // checkpoint of the state entering this chunk: prefetched by a bulk copy while the previous chunk was computed
-            if (lane == 0 && c > 1) issue_ck(c - 1);     // tile (c - 1) & 1 was last read two chunks ago
-            if (c > 0) mbar_wait(&sm.ckbar[c & 1], (ck_uses >> 1) & 1);
+            if (c > 1 && elect_one()) issue_ck(c - 1);   // tile (c - 1) & 1 was last read two chunks ago
+            if (c > 0) mbar_wait_a(sbase + OFF_CKBAR + 8u * (c & 1), (ck_uses >> 1) & 1);
             ck_uses += c > 0;
-            const float* ckt = &sm.ck[c & 1][sq * CKP + 2 * i];
-            auto load_ck = [&](int j) { return c > 0 ? *reinterpret_cast<const float2*>(ckt + (j ^ pm) * TR) : make_float2(0.f, 0.f); };
+            const float* ckt = &sm.ck[c & 1][sq * 4 * TR + 2 * i];
+            auto load_ck = [&](int j) {
+                return c > 0 ? *reinterpret_cast<const float2*>(ckt + (((j ^ pm) ^ (sq & 1)) << 4)) : make_float2(0.f, 0.f);
+            };
             const int own = (((2 * jw + (sq >> 1)) ^ rkey) << 2) + 2 * (sq & 1);   // word offset of (c0, c0 + 1) inside a tile row
             const int offA = i * WB + own, offB = (i + 8) * WB + own;
             {   // ---- prologue (once per element): delta', its sigmoid, delta' * u ----
@@ -519,7 +529,7 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     float a = dlA[e] + biasA, bb = dlB[e] + biasB, sa = 1.f, sb = 1.f;
-                    if (softplus) {
+                    if (SOFTPLUS) {
                         const SoftplusSig ra = softplus_sigmoid(a), rb = softplus_sigmoid(bb);
                         a = ra.sp; sa = ra.sig; bb = rb.sp; sb = rb.sig;
                     }
@@ -612,6 +622,13 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
                 *reinterpret_cast<float2*>(wd + offB) = make_float2(ddB0, ddB1);
             }
             __syncwarp();   // the union (rd) and the exchange tiles are free for the next chunk
+            if (refill >= 0) {   // the previous window's stores were issued a whole chunk ago: they have read their tiles by now
+                if (elect_one()) {
+                    tma_wait_read<0>();
+                    issue(refill);
+                }
+                refill = -1;
+            }
         }
         // ---- the window's outputs leave from its own tiles ----
         const int l_lo = win_lo(v);
@@ -636,28 +653,23 @@ sscan_bwd2_kernel(const __grid_constant__ b200_sscan_bwd_params q, const __grid_
                     }
                 }
             }
+            fence_proxy_async();
             __syncwarp();
-            if (lane == 0 && v + NSTB < nwin) {
-                fence_proxy_async();
-                issue(v + NSTB);
-            }
         } else {
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) {
-                tma_store_4d(&tm.du, wu, l_lo, r0, g, b);
-                tma_store_4d(&tm.ddelta, wd, l_lo, r0, g, b);
-                tma_reduce_add_4d(&tm.dB, wB, l_lo, 0, g, b);
-                tma_reduce_add_4d(&tm.dC, wC, l_lo, 0, g, b);
+            if (elect_one()) {
+                const unsigned w = sbase + OFF_WIN + (unsigned)s * STAGE_BYTES;
+                tma_store_4d_a(&tm.du, w, l_lo, r0, g, b);
+                tma_store_4d_a(&tm.ddelta, w + TILE_BYTES, l_lo, r0, g, b);
+                tma_reduce_add_4d_a(&tm.dB, w + 3 * TILE_BYTES, l_lo, 0, g, b);
+                tma_reduce_add_4d_a(&tm.dC, w + 4 * TILE_BYTES, l_lo, 0, g, b);
                 tma_commit_group();
-                if (v + NSTB < nwin) {
-                    tma_wait_read<0>();   // the stores have left the stage: refill it
-                    issue(v + NSTB);
-                }
             }
         }
+        if (v + NSTB < nwin) refill = v + NSTB;   // this stage is refilled once its stores have read it
     }
-    if (lane == 0) tma_wait_read<0>();
+    if (elect_one()) tma_wait_read<0>();   // elect.sync is deterministic: the thread that committed every store group
 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -734,10 +746,17 @@ bool try_fwd(const b200_sscan_fwd_params* p, cudaStream_t st, int* rc) {
     if (!make_fwd_maps(&tm, p, &tx, &zf)) return false;
     const int rpg = p->dim / p->n_groups;
     const long long nt = (long long)p->batch * p->n_groups * ((rpg + TR - 1) / TR);
-    (void)func_attr_per_device((const void*)sscan_fwd2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    (void)func_attr_per_device((const void*)sscan_fwd2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (p->z) sscan_fwd2_kernel<true><<<(unsigned)nt, 32, 0, st>>>(*p, tm, tx, zf);
-    else sscan_fwd2_kernel<false><<<(unsigned)nt, 32, 0, st>>>(*p, tm, tx, zf);
+    auto launch = [&](auto kernel) {
+        (void)func_attr_per_device((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        kernel<<<(unsigned)nt, 32, 0, st>>>(*p, tm, tx, zf);
+    };
+    if (p->z) {
+        if (p->delta_softplus) launch(sscan_fwd2_kernel<true, true>);
+        else launch(sscan_fwd2_kernel<true, false>);
+    } else {
+        if (p->delta_softplus) launch(sscan_fwd2_kernel<false, true>);
+        else launch(sscan_fwd2_kernel<false, false>);
+    }
     *rc = check_launch("sscan_fwd2_kernel");
     return true;
 }
@@ -781,8 +800,10 @@ bool try_bwd(const b200_sscan_bwd_params* q, cudaStream_t st, int* rc) {
     if (!make_bwd_maps(&tm, q, &tx, &zf)) return false;
     const int rpg = p->dim / p->n_groups;
     const long long nt = (long long)p->batch * p->n_groups * ((rpg + TR - 1) / TR);
-    (void)func_attr_per_device((const void*)sscan_bwd2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    sscan_bwd2_kernel<<<(unsigned)nt, 32, 0, st>>>(*q, tm, tx, zf);
+    (void)func_attr_per_device((const void*)sscan_bwd2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    (void)func_attr_per_device((const void*)sscan_bwd2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (p->delta_softplus) sscan_bwd2_kernel<true><<<(unsigned)nt, 32, 0, st>>>(*q, tm, tx, zf);
+    else sscan_bwd2_kernel<false><<<(unsigned)nt, 32, 0, st>>>(*q, tm, tx, zf);
     *rc = check_launch("sscan_bwd2_kernel");
     return true;
 }
