@@ -386,7 +386,8 @@ def run_cuda(args):
     net = build_model(args.model).to(dev)
     use_graph = not args.no_graph
     step = TrainStep(net, lr=1e-4, autocast=torch.bfloat16, ddp=ddp, local_rank=local_rank, graph=use_graph,
-                     bucket_cap_mb=args.bucket_mb, grad_bf16=args.grad_bf16, broadcast_buffers=args.broadcast_buffers)
+                     bucket_cap_mb=args.bucket_mb, grad_bf16=args.grad_bf16, broadcast_buffers=args.broadcast_buffers,
+                     ddp_impl=args.ddp_impl)
     model = step.model
     B = args.batch
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
@@ -491,8 +492,12 @@ def run_cuda(args):
                 "data": "synthetic",
                 "config": {"workload": cfg["workload"], "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
                            "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-4 (fused)", "launch": graph_note,
-                           "ddp": (f"bucket_cap_mb {args.bucket_mb}, static_graph, gradient_as_bucket_view, broadcast_buffers={args.broadcast_buffers}, "
-                                   f"{'bf16' if args.grad_bf16 else 'fp32'} gradient all-reduce") if ddp else None,
+                           "ddp": (None if not ddp else
+                                   (f"FlatGradSync: one fp32 gradient buffer, {len(step.sync.slices)} chunked NCCL all-reduces (avg) of "
+                                    f"{[round(b_ / 2**20, 1) for b_ in step.sync.chunk_bytes()]} MiB launched from accumulate-grad hooks on a side "
+                                    f"stream, captured in the step graph") if step.sync is not None else
+                                   (f"DistributedDataParallel: bucket_cap_mb {args.bucket_mb}, static_graph, gradient_as_bucket_view, "
+                                    f"broadcast_buffers={args.broadcast_buffers}, {'bf16' if args.grad_bf16 else 'fp32'} gradient all-reduce")),
                            "scan_io": "fp32 (as the reference calls it), fp32 state",
                            "l2": "per-step activations (> 10 GB) exceed the 126 MB L2; no explicit flush"},
                 "e2e": {"value": round(total / (ms_e2e / 1e3), 2), "unit": UNIT,
@@ -528,7 +533,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--model", default="medmamba_t", choices=sorted(MODELS), help="medmamba_t = BASELINE.json configs[1] (default), medssd = configs[2]")
-    ap.add_argument("--bucket-mb", type=int, default=8, help="DDP bucket size (N > 1)")
+    ap.add_argument("--ddp-impl", default="flat", choices=["flat", "torch"],
+                    help="N > 1: 'flat' = train_step.FlatGradSync (one gradient buffer, a few chunked all-reduces), 'torch' = DistributedDataParallel")
+    ap.add_argument("--bucket-mb", type=int, default=8, help="DistributedDataParallel bucket size (--ddp-impl torch)")
     ap.add_argument("--grad-bf16", action="store_true", help="bf16-compressed gradient all-reduce (N > 1)")
     ap.add_argument("--broadcast-buffers", action="store_true",
                     help="re-enable DDP's per-step broadcast of rank 0's BatchNorm statistics (N > 1; see train_step.py)")

@@ -27,18 +27,35 @@ def _data():
     return torch.randn(4, 3, 32, 32, generator=g), torch.randint(0, 6, (4,), generator=g)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, impl="torch"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     net = _net()
-    ddp = torch.nn.parallel.DistributedDataParallel(net)
     x, y = _data()
     per = x.shape[0] // world
     xs, ys = x[rank * per:(rank + 1) * per], y[rank * per:(rank + 1) * per]   # DistributedSampler-style shard
-    loss = torch.nn.functional.cross_entropy(ddp(xs), ys)
-    loss.backward()
+    if impl == "torch":
+        ddp = torch.nn.parallel.DistributedDataParallel(net)
+        loss = torch.nn.functional.cross_entropy(ddp(xs), ys)
+        loss.backward()
+    else:   # the product's reducer (train_step.FlatGradSync): flat gradient buffer, chunked all-reduce from accumulate hooks
+        from medical_image_classification_b200.train_step import FlatGradSync
+        if rank == 1:   # construction must bring every rank to rank 0's parameters
+            with torch.no_grad():
+                for p_ in net.parameters():
+                    p_.add_(1.0)
+        sync = FlatGradSync(net)
+        assert len(sync.slices) >= 2 and sum(sync.need) == len(sync.params)
+        for _ in range(2):   # twice: begin() must reset the in-place accumulated buffer
+            sync.begin()
+            loss = torch.nn.functional.cross_entropy(net(xs), ys)
+            loss.backward()
+            assert any(sync.sent[:-1]) or len(sync.sent) == 1   # early chunks left from the hooks, during backward
+            sync.finish()
+            assert all(sync.sent)
+        assert all(p_.grad.data_ptr() >= sync.flat.data_ptr() for p_ in net.parameters())
     t = torch.tensor([float(loss)])
     dist.all_reduce(t)           # the bench's max/mean-over-ranks plumbing
     if rank == 0:
@@ -47,13 +64,17 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_matches_single_process(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("impl", ["torch", "flat"])
+def test_two_rank_gloo_matches_single_process(tmp_path, impl):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "r0.pt")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, impl), nprocs=2, join=True)
     got = torch.load(out)
     net = _net()
     x, y = _data()
