@@ -308,6 +308,7 @@ __device__ __forceinline__ void gemm_pipeline(Smem& sm, int nkt, LA la, LB lb, S
 // ---- engine A: warp-level mma.sync tiles (accumulators in registers) ---------------------------------------
 struct MmaEngine {
     using Shared = Smem;
+    static constexpr int MIN_CTAS = 2;   // accumulators in registers: 128 registers per thread
     Acc acc;
     static __device__ __forceinline__ Shared& smem() {
         extern __shared__ __align__(1024) unsigned char raw[];
@@ -392,8 +393,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 }  // namespace tc
 
+#ifndef B200_SSD_TC_CTAS
+#define B200_SSD_TC_CTAS 2
+#endif
 struct TcEngine {
     using Shared = tc::Shared;
+    // resident CTAs per SM.  Measured at the MedSSD stage-0 shape, TF32 mode (fwd / bwd of one call): 1 CTA 5.06 / 14.3 ms,
+    // 2 CTAs 3.90 / 10.9 ms, 3 CTAs (80 registers, no spills, 66 KB of shared memory each) 4.27 / 11.7 ms -- beyond two the
+    // staging stores saturate the shared-memory pipe (56-65 % of its wavefront peak at two CTAs) instead of hiding more latency
+    static constexpr int MIN_CTAS = B200_SSD_TC_CTAS;
     uint32_t tmem;
     uint32_t issued[2], waited[2];
     bool started, x3_;
@@ -401,23 +409,26 @@ struct TcEngine {
         extern __shared__ __align__(1024) unsigned char raw[];
         return *reinterpret_cast<Shared*>(raw);
     }
-    // register-tile mappings (vid = it * 256 + tid).  !KI: as load_raw (k = 4 (vid % 8), i = vid / 8).
-    // KI: a warp covers 8 row-quads x 4 consecutive k:  i = 32 (blk % (TI/32)) + 4 (vid % 8),  k = 4 (blk / (TI/32)) + (vid / 8) % 4
-    template <int TI> static __device__ __forceinline__ void ki_map(int vid, int& i, int& k) {
-        const int blk = vid >> 5;
-        i = 32 * (blk % (TI / 32)) + 4 * (vid & 7);
-        k = 4 * (blk / (TI / 32)) + ((vid >> 3) & 3);
+    // register-tile mappings.  !KI: as load_raw (vid = it * 256 + tid: k = 4 (vid % 8), i = vid / 8).
+    // KI (the source is contiguous along i): a thread owns a block of 4 rows x NV consecutive k -- row quad iq = tid % (TI/4),
+    // k = NV (tid / (TI/4)) + it -- so its NV 128-bit loads (one per k, lanes of a warp along i: 512-byte runs) become 4 stores
+    // of NV consecutive k of ONE row each (one STS.128 for the 128-row operand, one STS.64 for the 64-row operand) in the
+    // K-major core-matrix layout.  The first version gave a thread 4 rows x 1 k per load and stored single words:
+    // 16 STS.32 per k-tile and thread for the 128-row operand instead of 4 STS.128.
+    template <int TI> static __device__ __forceinline__ void ki_map(int tid, int& i, int& k0) {
+        i = 4 * (tid % (TI / 4));
+        k0 = RegTile<TI>::NV * (tid / (TI / 4));
     }
     template <int TI, bool KI, typename T>
     static __device__ __forceinline__ void load(RegTile<TI>& r, const T* p, int64_t si, int64_t sk, int ni, int nk, bool vec) {
         if constexpr (!KI) {
             load_raw<TI, false>(r, p, si, sk, ni, nk, vec);
         } else {
-            const int tid = threadIdx.x;
+            int i, k0;
+            ki_map<TI>(threadIdx.x, i, k0);
 #pragma unroll
             for (int it = 0; it < RegTile<TI>::NV; ++it) {
-                int i, k;
-                ki_map<TI>(it * NTHR + tid, i, k);
+                const int k = k0 + it;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (k < nk && i < ni) {
                     const T* q = p + (int64_t)i * si + (int64_t)k * sk;
@@ -464,21 +475,39 @@ struct TcEngine {
                     t = h;
                 }
                 *reinterpret_cast<float4*>(d.hi + off) = t;
-            } else {
-                int i, k;
-                ki_map<TI>(vid, i, k);
-                const float t[4] = {xf(i, k, v.x), xf(i + 1, k, v.y), xf(i + 2, k, v.z), xf(i + 3, k, v.w)};
+            }
+        }
+        if constexpr (KI) {
+            constexpr int NV = RegTile<TI>::NV;   // 4 (128-row operand) or 2 (64-row operand) consecutive k per row
+            int i, k0;
+            ki_map<TI>(tid, i, k0);
+            float t[4][NV];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int off = (k >> 2) * LBO + ((i + j) >> 3) * tc::SBO + ((i + j) & 7) * 16 + (k & 3) * 4;
-                    float a = t[j];
-                    if (d.x3) {
-                        const float h = hi_part(a);
-                        *reinterpret_cast<float*>(d.lo + off) = a - h;
-                        a = h;
+            for (int it = 0; it < NV; ++it) {
+                const float4 v = r.v[it];
+                t[0][it] = xf(i, k0 + it, v.x);
+                t[1][it] = xf(i + 1, k0 + it, v.y);
+                t[2][it] = xf(i + 2, k0 + it, v.z);
+                t[3][it] = xf(i + 3, k0 + it, v.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int off = (k0 >> 2) * LBO + ((i + j) >> 3) * tc::SBO + ((i + j) & 7) * 16 + (k0 & 3) * 4;
+                float h[NV];
+#pragma unroll
+                for (int it = 0; it < NV; ++it) h[it] = t[j][it];
+                if (d.x3) {
+                    float lo[NV];
+#pragma unroll
+                    for (int it = 0; it < NV; ++it) {
+                        h[it] = hi_part(t[j][it]);
+                        lo[it] = t[j][it] - h[it];
                     }
-                    *reinterpret_cast<float*>(d.hi + off) = a;
+                    if constexpr (NV == 4) *reinterpret_cast<float4*>(d.lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    else *reinterpret_cast<float2*>(d.lo + off) = make_float2(lo[0], lo[1]);
                 }
+                if constexpr (NV == 4) *reinterpret_cast<float4*>(d.hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                else *reinterpret_cast<float2*>(d.hi + off) = make_float2(h[0], h[1]);
             }
         }
     }
@@ -644,7 +673,7 @@ __global__ void __launch_bounds__(MAXQ) dt_cumsum_kernel(const T* dt, int64_t s0
 //   MODE 1 (d states):      src_x = dout, src_b = C,  w_s = exp(cs_s)
 // GEMM: M = n (128 per tile), N = p (64 per tile), K = s.
 template <typename T, int MODE, class E>
-__global__ void __launch_bounds__(NTHR, 2) chunk_state_kernel(View4<T> X, View4<T> Bv, Dims d, Ws ws, float* out, int x3) {
+__global__ void __launch_bounds__(NTHR, E::MIN_CTAS) chunk_state_kernel(View4<T> X, View4<T> Bv, Dims d, Ws ws, float* out, int x3) {
     typename E::Shared& sm = E::smem();
     const int ntn = (d.N + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
     int bid = blockIdx.x;
@@ -736,7 +765,7 @@ __global__ void state_pass_kernel_scalar(Dims d, Ws ws, const float* init, float
 
 // ---- K4: CB[l][s] = sum_n C[l, n] B[s, n]  per (b, c, g); only tiles touching s <= l ------------
 template <typename T, class E>
-__global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, Dims d, Ws ws, int x3) {
+__global__ void __launch_bounds__(NTHR, E::MIN_CTAS) cb_kernel(View4<T> Cv, View4<T> Bv, Dims d, Ws ws, int x3) {
     typename E::Shared& sm = E::smem();
     const int ntm = (d.Q + BM - 1) / BM, ntn = (d.Q + BN - 1) / BN;
     int bid = blockIdx.x;
@@ -773,7 +802,7 @@ __global__ void __launch_bounds__(NTHR, 2) cb_kernel(View4<T> Cv, View4<T> Bv, D
 // per row and one per column, precomputed once per CTA; inside the 32 x 32 diagonal block it is evaluated
 // exactly per element (no overflow whatever the decay rate).
 template <typename T, class E>
-__global__ void __launch_bounds__(NTHR, 2) chunk_scan_kernel(View4<T> X, View4<T> Cv, const float* D, Dims d, Ws ws, T* out,
+__global__ void __launch_bounds__(NTHR, E::MIN_CTAS) chunk_scan_kernel(View4<T> X, View4<T> Cv, const float* D, Dims d, Ws ws, T* out,
                                                              int64_t o0, int64_t o1, int64_t o2, int64_t o3, int has_init, int x3) {
     typename E::Shared& sm = E::smem();
     const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
@@ -1036,7 +1065,7 @@ __global__ void __launch_bounds__(NTHR, 2) dx_kernel(View4<T> X, View4<T> Bv, Vi
 // B3 on the tcgen05 engine: same contractions, operands staged through registers (128-bit loads where the view
 // allows) into UMMA tiles, accumulator row = one thread in the epilogue (row sums need no shuffles).
 template <typename T>
-__global__ void __launch_bounds__(NTHR, 2) dx_kernel_tc(View4<T> X, View4<T> Bv, View4<T> DO, View4<T> OUT, const float* D, Dims d, Ws ws,
+__global__ void __launch_bounds__(NTHR, TcEngine::MIN_CTAS) dx_kernel_tc(View4<T> X, View4<T> Bv, View4<T> DO, View4<T> OUT, const float* D, Dims d, Ws ws,
                                                         const float* G, float* dx, float* ddtp_exp, float* dcs_pos, float* dD, int x3) {
     using E = TcEngine;
     E::Shared& sm = E::smem();
@@ -1257,7 +1286,7 @@ __global__ void __launch_bounds__(NTHR, 2) dbc_kernel(View4<T> X, View4<T> Bv, V
 
 // B5 on the tcgen05 engine.
 template <typename T>
-__global__ void __launch_bounds__(NTHR, 2) dbc_kernel_tc(View4<T> X, View4<T> Bv, View4<T> Cv, View4<T> DO, Dims d, Ws ws,
+__global__ void __launch_bounds__(NTHR, TcEngine::MIN_CTAS) dbc_kernel_tc(View4<T> X, View4<T> Bv, View4<T> Cv, View4<T> DO, Dims d, Ws ws,
                                                          const float* dcb_all, const float* G, float* dB, float* dC, int x3) {
     using E = TcEngine;
     E::Shared& sm = E::smem();
