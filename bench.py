@@ -383,6 +383,8 @@ def run_cuda(args):
                     "host_cores": os.cpu_count()}
 
     from medical_image_classification_b200.train_step import TrainStep
+    from medical_image_classification_b200 import models as _models
+    _models.SS_Conv_SSM.overlap_branches = not args.no_overlap
     net = build_model(args.model).to(dev)
     use_graph = not args.no_graph
     step = TrainStep(net, lr=1e-4, autocast=torch.bfloat16, ddp=ddp, local_rank=local_rank, graph=use_graph,
@@ -492,6 +494,8 @@ def run_cuda(args):
                 "data": "synthetic",
                 "config": {"workload": cfg["workload"], "global_batch": B * world, "per_gpu_batch": B, "image": "3x224x224",
                            "parallelism": f"dp{world}", "optimizer": "Adam lr 1e-4 (fused)", "launch": graph_note,
+                           "streams": ("conv branch of every block on a side stream, SS2D branch on the main stream (fork / join captured in the graph)"
+                                       if not args.no_overlap else "single stream"),
                            "ddp": (None if not ddp else
                                    (f"FlatGradSync: one fp32 gradient buffer, {len(step.sync.slices)} chunked NCCL all-reduces (avg) of "
                                     f"{[round(b_ / 2**20, 1) for b_ in step.sync.chunk_bytes()]} MiB launched from accumulate-grad hooks on a side "
@@ -533,6 +537,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--model", default="medmamba_t", choices=sorted(MODELS), help="medmamba_t = BASELINE.json configs[1] (default), medssd = configs[2]")
+    ap.add_argument("--no-overlap", action="store_true", help="run the blocks' convolution branch on the SS2D branch's stream (A/B of models.SS_Conv_SSM.overlap_branches)")
     ap.add_argument("--ddp-impl", default="flat", choices=["flat", "torch"],
                     help="N > 1: 'flat' = train_step.FlatGradSync (one gradient buffer, a few chunked all-reduces), 'torch' = DistributedDataParallel")
     ap.add_argument("--bucket-mb", type=int, default=8, help="DistributedDataParallel bucket size (--ddp-impl torch)")

@@ -125,6 +125,19 @@ class ShuffleCatAddFn(torch.autograd.Function):
         return dleft, dx, dout
 
 
+_BRANCH_STREAMS = {}
+
+
+def branch_stream(device):
+    """The side stream (one per device) on which the blocks' convolution branch runs while the SS2D branch runs on the
+    caller's stream."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _BRANCH_STREAMS.get(key)
+    if st is None:
+        st = _BRANCH_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 class SS_Conv_SSM(nn.Module):
     """Two-branch block: half the channels through conv3x3-conv3x3-conv1x1, half through
     LayerNorm -> SS2D; concat, channel shuffle, residual."""
@@ -148,19 +161,40 @@ class SS_Conv_SSM(nn.Module):
             nn.ReLU(),
         )
 
+    # The two branches of a block are independent until the concatenation (MedMamba.py:533-538).  On CUDA the convolution branch
+    # (cuDNN convolutions, BatchNorm, ReLU: bandwidth-bound library kernels) is issued on a side stream and the SS2D branch on the
+    # caller's: the scan kernels leave issue slots, DRAM bandwidth and -- at the end of their single wave -- whole SMs idle, which
+    # the other branch's kernels fill.  Autograd replays each op on its forward stream, so the backward overlaps the same way, and
+    # the fork / join is captured like any other dependency when the step is recorded in a CUDA graph.
+    overlap_branches = True
+
+    def _conv_branch(self, left):
+        # the conv branch consumes channels-last data: on CUDA keep it in torch.channels_last (cuDNN / BatchNorm run NHWC
+        # natively: no NCHW<->NHWC converter kernels; measured 33.2 -> 29.2 ms per MedMamba-T step)
+        left = left.permute(0, 3, 1, 2)
+        left = left.contiguous(memory_format=torch.channels_last)
+        return self.conv33conv33conv11(left)
+
     def forward(self, input):
         left, right = split_halves(input)
+        side = None
+        if self.overlap_branches and input.is_cuda:
+            cur = torch.cuda.current_stream(input.device)
+            side = branch_stream(input.device)
+            side.wait_stream(cur)                          # fork: `left` is ready on the caller's stream
+            with torch.cuda.stream(side):
+                left = self._conv_branch(left)
         if right.dtype in (torch.float32, torch.bfloat16) and isinstance(self.ln_1, nn.LayerNorm) and right.shape[-1] <= 1024:
             from .ss2d import layer_norm_rows
             normed = layer_norm_rows(right, self.ln_1)     # pre-norm, the right half read in place (csrc/lngate.cu)
         else:
             normed = self.ln_1(right)
         x = self.drop_path(self.self_attention(normed))
-        # the conv branch consumes channels-last data: on CUDA keep it in torch.channels_last (cuDNN / BatchNorm run NHWC
-        # natively: no NCHW<->NHWC converter kernels; measured 33.2 -> 29.2 ms per MedMamba-T step)
-        left = left.permute(0, 3, 1, 2)
-        left = left.contiguous(memory_format=torch.channels_last)
-        left = self.conv33conv33conv11(left)
+        if side is not None:
+            cur.wait_stream(side)                          # join
+            left.record_stream(cur)                        # allocated on the side stream, consumed (and later freed) on this one
+        else:
+            left = self._conv_branch(left)
         if (input.dtype in (torch.float32, torch.bfloat16) and left.dtype in (torch.float32, torch.bfloat16)
                 and x.dtype in (torch.float32, torch.bfloat16) and left.shape[0] <= 65535):
             return ShuffleCatAddFn.apply(left, x, input)   # cat + channel shuffle + residual in one pass (csrc/glue.cu)

@@ -55,8 +55,9 @@ class FlatGradSync:
     One flat fp32 buffer holds every gradient, ordered as backward produces them and cut into a few contiguous chunks.  During
     backward autograd hands each parameter its gradient as usual (no per-parameter copy or add kernel: with `p.grad is None` the
     engine just keeps the tensor the backward kernel wrote).  A post-accumulate hook per parameter counts arrivals; when a chunk is
-    complete its gradients are gathered into the buffer with ONE multi-tensor copy, the chunk is all-reduced (average) with ONE
-    NCCL call on `self.stream`, and `p.grad` is re-pointed at the parameter's view of the buffer, which is what the optimizer
+    complete its gradients are gathered into the buffer with ONE multi-tensor copy and the chunk is all-reduced (average) with ONE
+    NCCL call, both on `self.stream` after every compute stream that produced one of them (the model runs its two branches on two
+    streams), and `p.grad` is re-pointed at the parameter's view of the buffer, which is what the optimizer
     reads.  `finish()` sends what is left (parameters that received no gradient count as zero) and joins the side stream.
     Everything is stream-ordered, so the whole exchange is captured in the step's CUDA graph.  (DistributedDataParallel, and a first
     version of this class that let autograd accumulate into the views, pay one small kernel per parameter per step -- ~230 for
@@ -94,6 +95,7 @@ class FlatGradSync:
         self.need = [hi - lo for lo, hi in self.ranges]
         self.got = [0] * len(self.ranges)
         self.sent = [False] * len(self.ranges)
+        self.seen = [set() for _ in self.ranges]
         self.active = False
         self.stream = torch.cuda.Stream(device=self.dev) if self.dev.type == "cuda" else None
         self.avg = dist.get_backend(process_group) == "nccl"
@@ -111,6 +113,8 @@ class FlatGradSync:
     def _make_hook(self, c):
         def hook(_p):
             if self.active:
+                if self.stream is not None:                  # gradients of one chunk may come from several streams (models.branch_stream)
+                    self.seen[c].add(torch.cuda.current_stream(self.dev))
                 self.got[c] += 1
                 if self.got[c] == self.need[c]:
                     self._send(c)
@@ -122,21 +126,31 @@ class FlatGradSync:
         self.sent[c] = True
         lo, hi = self.ranges[c]
         src = [p.grad for p in self.params[lo:hi]]
-        if any(g is None for g in src):                      # parameters outside this step's graph: their gradient is zero
+        if self.stream is None and any(g is None for g in src):   # parameters outside this step's graph: their gradient is zero
             self.slices[c].zero_()
         dst = [v for v, g in zip(self.views[lo:hi], src) if g is not None]
         src = [g for g in src if g is not None]
-        if src:
-            torch._foreach_copy_(dst, src)                   # one multi-tensor kernel (per ~100 tensors), not one copy per parameter
-        for p, v in zip(self.params[lo:hi], self.views[lo:hi]):
-            p.grad = v
         buf = self.slices[c]
         if self.stream is not None:
-            self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+            # gather and reduce on the side stream, after every stream that produced one of the chunk's gradients: an event recorded
+            # now on such a stream covers all of them (their kernels were enqueued before this hook ran)
+            self.seen[c].add(torch.cuda.current_stream(self.dev))
+            for st in self.seen[c]:
+                self.stream.wait_stream(st)
             with torch.cuda.stream(self.stream):
+                if any(g is None for g in (p.grad for p in self.params[lo:hi])):
+                    buf.zero_()
+                if src:
+                    torch._foreach_copy_(dst, src)           # one multi-tensor kernel (per ~100 tensors), not one copy per parameter
+                    for g in src:
+                        g.record_stream(self.stream)         # allocated on a compute stream, last read here
                 self._reduce(buf)
         else:
+            if src:
+                torch._foreach_copy_(dst, src)
             self._reduce(buf)
+        for p, v in zip(self.params[lo:hi], self.views[lo:hi]):
+            p.grad = v
 
     def _reduce(self, buf):
         if self.avg:
@@ -151,6 +165,7 @@ class FlatGradSync:
             p.grad = None
         self.got = [0] * len(self.ranges)
         self.sent = [False] * len(self.ranges)
+        self.seen = [set() for _ in self.ranges]
         self.active = True
 
     def finish(self):
