@@ -130,16 +130,25 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_silu_fwd_kernel(const TI
             const float* i2 = i1 + rowI;
             float* o = oc + r * W + w0;
             float a0 = i0[0], a1 = i0[DW_C], b0 = i1[0], b1 = i1[DW_C], e0 = i2[0], e1 = i2[DW_C];
-            for (int q = 0; q < n; ++q) {
-                const float a2 = i0[2 * DW_C], b2 = i1[2 * DW_C], e2 = i2[2 * DW_C];
-                float acc = bv;
-                acc = fmaf(k[0], a0, acc); acc = fmaf(k[1], a1, acc); acc = fmaf(k[2], a2, acc);
-                acc = fmaf(k[3], b0, acc); acc = fmaf(k[4], b1, acc); acc = fmaf(k[5], b2, acc);
-                acc = fmaf(k[6], e0, acc); acc = fmaf(k[7], e1, acc); acc = fmaf(k[8], e2, acc);
-                o[q] = acc * sigmoidf_(acc);
-                a0 = a1; a1 = a2; b0 = b1; b1 = b2; e0 = e1; e1 = e2;
-                i0 += DW_C; i1 += DW_C; i2 += DW_C;
+#define DW_FWD_STEP(q)                                                                                                    \
+    {                                                                                                                     \
+        const float a2 = i0[((q) + 2) * DW_C], b2 = i1[((q) + 2) * DW_C], e2 = i2[((q) + 2) * DW_C];                      \
+        float acc = bv;                                                                                                   \
+        acc = fmaf(k[0], a0, acc); acc = fmaf(k[1], a1, acc); acc = fmaf(k[2], a2, acc);                                  \
+        acc = fmaf(k[3], b0, acc); acc = fmaf(k[4], b1, acc); acc = fmaf(k[5], b2, acc);                                  \
+        acc = fmaf(k[6], e0, acc); acc = fmaf(k[7], e1, acc); acc = fmaf(k[8], e2, acc);                                  \
+        o[q] = acc * sigmoidf_(acc);                                                                                      \
+        a0 = a1; a1 = a2; b0 = b1; b1 = b2; e0 = e1; e1 = e2;                                                             \
+    }
+            // every model shape (W = 56 / 28 / 14 / 7) consists of full strips: the unrolled body turns the window rotation into
+            // register renaming and the addresses into immediates (the rolled loop spent ~a third of its instructions on both)
+            if (n == DW_SEG) {
+#pragma unroll
+                for (int q = 0; q < DW_SEG; ++q) DW_FWD_STEP(q)
+            } else {
+                for (int q = 0; q < n; ++q) DW_FWD_STEP(q)
             }
+#undef DW_FWD_STEP
         }
     }
     __syncthreads();
@@ -236,17 +245,24 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_silu_bwd_kernel(const fl
             const float* i2 = i1 + rowI;
             float* dq = dpc + r * WG + wc0;
             float a0 = i0[0], a1 = i0[DW_C], b0 = i1[0], b1 = i1[DW_C], e0 = i2[0], e1 = i2[DW_C];
-            for (int q = 0; q < n; ++q) {
-                const float a2 = i0[2 * DW_C], b2 = i1[2 * DW_C], e2 = i2[2 * DW_C];
-                float pre = bv;
-                pre = fmaf(k[0], a0, pre); pre = fmaf(k[1], a1, pre); pre = fmaf(k[2], a2, pre);
-                pre = fmaf(k[3], b0, pre); pre = fmaf(k[4], b1, pre); pre = fmaf(k[5], b2, pre);
-                pre = fmaf(k[6], e0, pre); pre = fmaf(k[7], e1, pre); pre = fmaf(k[8], e2, pre);
-                const float sg = sigmoid_fast(pre);
-                dq[q] *= sg * (1.f + pre * (1.f - sg));   // zero outside the image: g was zero-filled there
-                a0 = a1; a1 = a2; b0 = b1; b1 = b2; e0 = e1; e1 = e2;
-                i0 += DW_C; i1 += DW_C; i2 += DW_C;
+#define DW_BWD_A_STEP(q)                                                                                                  \
+    {                                                                                                                     \
+        const float a2 = i0[((q) + 2) * DW_C], b2 = i1[((q) + 2) * DW_C], e2 = i2[((q) + 2) * DW_C];                      \
+        float pre = bv;                                                                                                   \
+        pre = fmaf(k[0], a0, pre); pre = fmaf(k[1], a1, pre); pre = fmaf(k[2], a2, pre);                                  \
+        pre = fmaf(k[3], b0, pre); pre = fmaf(k[4], b1, pre); pre = fmaf(k[5], b2, pre);                                  \
+        pre = fmaf(k[6], e0, pre); pre = fmaf(k[7], e1, pre); pre = fmaf(k[8], e2, pre);                                  \
+        const float sg = sigmoid_fast(pre);                                                                               \
+        dq[q] *= sg * (1.f + pre * (1.f - sg)); /* zero outside the image: g was zero-filled there */                     \
+        a0 = a1; a1 = a2; b0 = b1; b1 = b2; e0 = e1; e1 = e2;                                                             \
+    }
+            if (n == DW_SEG) {
+#pragma unroll
+                for (int q = 0; q < DW_SEG; ++q) DW_BWD_A_STEP(q)
+            } else {
+                for (int q = 0; q < n; ++q) DW_BWD_A_STEP(q)
             }
+#undef DW_BWD_A_STEP
         }
     }
     __syncthreads();
@@ -270,25 +286,31 @@ __global__ void __launch_bounds__(DW_THREADS, 3) dwconv_silu_bwd_kernel(const fl
             float x00 = d0p[0], x01 = d0p[1], x10 = d1p[0], x11 = d1p[1], x20 = d2p[0], x21 = d2p[1];
             float y00 = i0[0], y01 = i0[DW_C], y10 = i1[0], y11 = i1[DW_C], y20 = i2[0], y21 = i2[DW_C];
             TI* o = dxin + ((int64_t)(b * H + h0 + r) * W + w0) * D + c0 + c;
-            for (int q = 0; q < n; ++q) {
-                const float x02 = d0p[q + 2], x12 = d1p[q + 2], x22 = d2p[q + 2];
-                const float y02 = i0[2 * DW_C], y12 = i1[2 * DW_C], y22 = i2[2 * DW_C];
-                // out(h + 1 - dr, w + 1 - dc) used in(h, w) with tap (dr, dc): acc = sum k[dr][dc] * dp[r + 2 - dr][w + 2 - dc]
-                float acc = k[0] * x22;
-                acc = fmaf(k[1], x21, acc); acc = fmaf(k[2], x20, acc);
-                acc = fmaf(k[3], x12, acc); acc = fmaf(k[4], x11, acc); acc = fmaf(k[5], x10, acc);
-                acc = fmaf(k[6], x02, acc); acc = fmaf(k[7], x01, acc); acc = fmaf(k[8], x00, acc);
-                const float dd = x11;
-                dk[0] = fmaf(dd, y00, dk[0]); dk[1] = fmaf(dd, y01, dk[1]); dk[2] = fmaf(dd, y02, dk[2]);
-                dk[3] = fmaf(dd, y10, dk[3]); dk[4] = fmaf(dd, y11, dk[4]); dk[5] = fmaf(dd, y12, dk[5]);
-                dk[6] = fmaf(dd, y20, dk[6]); dk[7] = fmaf(dd, y21, dk[7]); dk[8] = fmaf(dd, y22, dk[8]);
-                db += dd;
-                if (cok) stg_stream(o, acc);
-                o += D;
-                x00 = x01; x01 = x02; x10 = x11; x11 = x12; x20 = x21; x21 = x22;
-                y00 = y01; y01 = y02; y10 = y11; y11 = y12; y20 = y21; y21 = y22;
-                i0 += DW_C; i1 += DW_C; i2 += DW_C;
+            // out(h + 1 - dr, w + 1 - dc) used in(h, w) with tap (dr, dc): acc = sum k[dr][dc] * dp[r + 2 - dr][w + 2 - dc]
+#define DW_BWD_B_STEP(q)                                                                                                  \
+    {                                                                                                                     \
+        const float x02 = d0p[(q) + 2], x12 = d1p[(q) + 2], x22 = d2p[(q) + 2];                                           \
+        const float y02 = i0[((q) + 2) * DW_C], y12 = i1[((q) + 2) * DW_C], y22 = i2[((q) + 2) * DW_C];                   \
+        float acc = k[0] * x22;                                                                                           \
+        acc = fmaf(k[1], x21, acc); acc = fmaf(k[2], x20, acc);                                                           \
+        acc = fmaf(k[3], x12, acc); acc = fmaf(k[4], x11, acc); acc = fmaf(k[5], x10, acc);                               \
+        acc = fmaf(k[6], x02, acc); acc = fmaf(k[7], x01, acc); acc = fmaf(k[8], x00, acc);                               \
+        const float dd = x11;                                                                                             \
+        dk[0] = fmaf(dd, y00, dk[0]); dk[1] = fmaf(dd, y01, dk[1]); dk[2] = fmaf(dd, y02, dk[2]);                         \
+        dk[3] = fmaf(dd, y10, dk[3]); dk[4] = fmaf(dd, y11, dk[4]); dk[5] = fmaf(dd, y12, dk[5]);                         \
+        dk[6] = fmaf(dd, y20, dk[6]); dk[7] = fmaf(dd, y21, dk[7]); dk[8] = fmaf(dd, y22, dk[8]);                         \
+        db += dd;                                                                                                         \
+        if (cok) stg_stream(o + (int64_t)(q) * D, acc);                                                                   \
+        x00 = x01; x01 = x02; x10 = x11; x11 = x12; x20 = x21; x21 = x22;                                                 \
+        y00 = y01; y01 = y02; y10 = y11; y11 = y12; y20 = y21; y21 = y22;                                                 \
+    }
+            if (n == DW_SEG) {
+#pragma unroll
+                for (int q = 0; q < DW_SEG; ++q) DW_BWD_B_STEP(q)
+            } else {
+                for (int q = 0; q < n; ++q) DW_BWD_B_STEP(q)
             }
+#undef DW_BWD_B_STEP
         }
     }
     __syncthreads();   // red_s aliases in_s

@@ -30,3 +30,10 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
     torch.cuda.synchronize()
 print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=70, max_name_column_width=60, max_shapes_column_width=90))
 print(prof.key_averages(group_by_stack_n=6).table(sort_by="self_cuda_time_total", row_limit=60, max_name_column_width=50, max_src_column_width=110))
+# ---- the glue ops by input shape: where the small copies / fills / sums come from ----
+rows = [e for e in prof.key_averages(group_by_input_shape=True)
+        if e.key in ("aten::copy_", "aten::fill_", "aten::sum", "aten::add_", "aten::add", "aten::mul", "aten::cat", "aten::zero_")]
+rows.sort(key=lambda e: -e.self_device_time_total)
+print("glue ops by input shape (self CUDA us, calls, shapes):")
+for e in rows[:60]:
+    print(f"  {e.key:12s} {e.self_device_time_total:9.1f} us  x{e.count:3d}  {str(e.input_shapes)[:150]}")
