@@ -39,7 +39,9 @@ def _np(t):
 
 
 def sscan_case(name, batch, dim, N, L, G, has_D, has_bias, softplus, has_z=False, model_A=False,
-               bc_3d=False, with_grads=True, seed=0):
+               bc_3d=False, with_grads=True, seed=0, itype=torch.float32):
+    """itype: dtype of u / delta / B / C / z as in the reference's test grid (test_selective_scan.py:372-390: fp32, fp16, bf16;
+    A, D, delta_bias stay fp32).  The arrays are stored as float32 holding the rounded values, `itype` names the dtype."""
     iface = ref_import.load_selective_scan_interface()
     torch.manual_seed(seed)
     if model_A:
@@ -55,13 +57,19 @@ def sscan_case(name, batch, dim, N, L, G, has_D, has_bias, softplus, has_z=False
     u = torch.randn(batch, dim, L)
     delta = 0.5 * torch.rand(batch, dim, L)
     g = torch.randn(batch, dim, L)
+    if itype != torch.float32:
+        Bm, Cm, u, delta, g = (t.to(itype) for t in (Bm, Cm, u, delta, g))
+        z = None if z is None else z.to(itype)
     leaves = [t for t in (u, delta, A, Bm, Cm, D, z, bias) if t is not None]
     for t in leaves:
         t.requires_grad_(with_grads)
     out, last = iface.selective_scan_ref(u, delta, A, Bm, Cm, D, z=z, delta_bias=bias,
                                          delta_softplus=softplus, return_last_state=True)
+    _np = lambda t: None if t is None else t.detach().float().cpu().numpy().copy()   # noqa: E731  (16-bit tensors -> float32 values)
     rec = dict(u=_np(u), delta=_np(delta), A=_np(A), B=_np(Bm), C=_np(Cm), g=_np(g),
                out=_np(out), last_state=_np(last), delta_softplus=np.array(int(softplus)))
+    if itype != torch.float32:
+        rec["itype"] = np.array(str(itype).replace("torch.", ""))
     if D is not None:
         rec["D"] = _np(D)
     if z is not None:
@@ -79,6 +87,14 @@ def sscan_case(name, batch, dim, N, L, G, has_D, has_bias, softplus, has_z=False
             rec["ddelta_bias"] = _np(bias.grad)
     np.savez_compressed(os.path.join(OUT, f"sscan_{name}.npz"), **rec)
     print("wrote", name, {k: v.shape for k, v in rec.items() if hasattr(v, "shape")})
+
+
+def sscan_extra_cases():
+    """More of the reference's own test grid (test_selective_scan.py:372-390: seqlen up to 4096, itype fp32 / fp16 / bf16)."""
+    sscan_case("long_L4096", 1, 8, 16, 4096, 1, True, True, True, with_grads=False)
+    sscan_case("grads_L1024", 1, 8, 16, 1024, 2, True, True, True, seed=3)
+    sscan_case("fp16_L256", 2, 24, 16, 256, 2, True, True, True, seed=4, itype=torch.float16)
+    sscan_case("bf16_L256", 2, 24, 16, 256, 2, True, True, True, seed=5, itype=torch.bfloat16)
 
 
 def ss2d_case(name, d_model, H, W, batch, seed=0):
@@ -345,6 +361,9 @@ def main():
     if "--crossmamba-only" in sys.argv:
         crossmamba_case("d32_6x5", 32, 8, 16, 6, 5, 2)
         return
+    if "--sscan-extra" in sys.argv:
+        sscan_extra_cases()
+        return
     if "--ssd-only" in sys.argv:
         ss2d_ssd_case("d32_7x5", 32, 8, 16, 7, 5, 2)
         ss2d_ssd_case("d64_6x6", 64, 16, 64, 6, 6, 1)
@@ -361,6 +380,7 @@ def main():
     sscan_case("z_L130", 2, 16, 8, 130, 1, True, True, True, has_z=True, bc_3d=True)
     # longer than the reference kernel's 2048-step chunk (selective_scan.cpp:307); forward only
     sscan_case("long_L2100", 1, 8, 16, 2100, 1, True, True, True, with_grads=False)
+    sscan_extra_cases()
     ss2d_case("d8_7x5", 8, 7, 5, 2)
     ss2d_case("d16_4x6", 16, 4, 6, 1)
     vssm_case()

@@ -91,6 +91,20 @@ def test_ssd_fwd_bwd_matches_oracle(case, model_layout):
     assert all(v < (2e-4 if k in loose else 2e-5) for k, v in errs.items()), errs
 
 
+@pytest.mark.parametrize("chunk", [16, 512, 48])
+def test_ssd_any_chunk_size_mamba_ssm_accepts(chunk):
+    """mamba_ssm takes any power-of-two chunk_size >= 16; the product maps it to a length its kernels tile (the result does not
+    depend on it) instead of rejecting it (round-1 review)."""
+    from medical_image_classification_b200.ssd_combined import mamba_chunk_scan_combined
+    d = make(1, 150, 4, 16, 1, 24, seed=chunk)
+    t = {k: to_dev(v, False) for k, v in d.items() if k != "dout"}
+    out = mamba_chunk_scan_combined(t["x"], t["dt"], t["A"], t["B"], t["C"], chunk, D=t["D"], dt_bias=t["dt_bias"], dt_softplus=True)
+    out.backward(torch.tensor(d["dout"], device="cuda"))
+    ref, _ = oracle.ssd_fwd(d["x"], d["dt"], d["A"], d["B"], d["C"], D=d["D"], dt_bias=d["dt_bias"], dt_softplus=True)
+    g = oracle.ssd_bwd(d["x"], d["dt"], d["A"], d["B"], d["C"], D=d["D"], dt_bias=d["dt_bias"], dt_softplus=True, dout=d["dout"])
+    assert rel(out, ref) < 2e-5 and rel(t["x"].grad, g["dx"]) < 2e-5 and rel(t["B"].grad, g["dB"]) < 2e-5
+
+
 def test_ssd_chunk_size_invariance_and_tf32_mode():
     from medical_image_classification_b200 import ssd_combined
     d = make(2, 200, 4, 64, 1, 64, seed=7)
