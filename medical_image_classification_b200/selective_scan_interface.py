@@ -236,11 +236,39 @@ class SelectiveScanFn(torch.autograd.Function):
                 None, None, None, None)
 
 
+MAX_DSTATE_PER_CALL = 16     # one kernel call carries 16 states per row in registers (csrc/sscan*.cu)
+MAX_DSTATE = 256             # the reference's limit (selective_scan.cpp:262)
+
+
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                       return_last_state=False):
     """if return_last_state is True, returns (out, last_state); last_state has shape
-    (batch, dim, dstate) and gets no gradient (reference selective_scan_interface.py:83-89)."""
-    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+    (batch, dim, dstate) and gets no gradient (reference selective_scan_interface.py:83-89).
+
+    dstate up to 256 like the reference (selective_scan.cpp:262).  The recurrence is independent per state and y is a sum over
+    states, so wider state spaces (no model of the reference repo uses one: every SS2D has d_state 16) run as ceil(dstate / 16)
+    calls on 16-state slices of A, B and C whose outputs add up; D u, the z gate and the concatenation of last_state are applied
+    once around them with tensor ops, and autograd sums the slices' gradients of u, delta and delta_bias."""
+    N = A.shape[1] if hasattr(A, "shape") and A.dim() == 2 else 0
+    if N <= MAX_DSTATE_PER_CALL:
+        return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+    if N > MAX_DSTATE:
+        raise RuntimeError(f"selective_scan: dstate {N} > {MAX_DSTATE} (the reference's limit, selective_scan.cpp:262)")
+    sdim = B.dim() - 2                                       # the state dimension of B / C: (b, n, l) or (b, g, n, l)
+    y, lasts = None, []
+    for n0 in range(0, N, MAX_DSTATE_PER_CALL):
+        n1 = min(N, n0 + MAX_DSTATE_PER_CALL)
+        r = SelectiveScanFn.apply(u, delta, A[:, n0:n1], B.narrow(sdim, n0, n1 - n0), C.narrow(sdim, n0, n1 - n0), None, None,
+                                  delta_bias, delta_softplus, return_last_state)
+        if return_last_state:
+            r, last = r
+            lasts.append(last)
+        y = r if y is None else y + r
+    if D is not None:
+        y = y + (u * D.to(u.dtype).view(1, -1, 1)).to(y.dtype)
+    if z is not None:
+        y = y * torch.nn.functional.silu(z.to(y.dtype))
+    return (y, torch.cat(lasts, dim=-1)) if return_last_state else y
 
 
 def selective_scan_dirs_fn(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False,

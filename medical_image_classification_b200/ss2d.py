@@ -269,7 +269,9 @@ class SS2D(nn.Module):
         self.out_norm = nn.LayerNorm(D)
         self.out_proj = nn.Linear(D, d_model, bias=bias, **fk)
         self.dropout = nn.Dropout(dropout) if dropout > 0.0 else None
-        self.forward_core = self.forward_core_fused
+        # the fused core keeps 16 states per row in registers; wider state spaces (unused by the reference's models) take the
+        # operator-API data flow, where selective_scan_fn runs them as 16-state slices
+        self.forward_core = self.forward_core_fused if d_state <= 16 else self.forward_core_api
 
     # ---- the hot path --------------------------------------------------------------------------
     @staticmethod

@@ -217,3 +217,28 @@ def test_fused_core_equals_api_core_at_model_plane_sizes(hw):
     assert relerr(dx1, dx2.cpu().numpy()) < 5e-5
     for k in g1:
         assert relerr(g1[k], g2[k].cpu().numpy()) < 5e-5, k
+
+
+def test_ss2d_wide_state_space_matches_cpu_tree():
+    """SS2D(d_state > 16) (the reference allows up to 256, selective_scan.cpp:262): the module falls back to the operator-API data
+    flow and the 16-state slices of selective_scan_fn; checked against the eager CPU tree (oracle/cpu_path.py) with the same weights."""
+    from oracle.cpu_path import bind_cpu_core
+    from medical_image_classification_b200.ss2d import SS2D
+    torch.manual_seed(0)
+    ref = SS2D(d_model=8, d_state=24)
+    m = SS2D(d_model=8, d_state=24)
+    m.load_state_dict(ref.state_dict())
+    assert bind_cpu_core(ref) == 1
+    x = torch.randn(2, 5, 6, 8)
+    g = torch.randn(2, 5, 6, 8)
+    xr = x.clone().requires_grad_()
+    ref(xr).backward(g)
+    m = m.cuda()
+    xc = x.cuda().requires_grad_()
+    out = m(xc)
+    out.backward(g.cuda())
+    rel = lambda a, b: float((a.detach().cpu().double() - b.detach().double()).abs().max() / b.detach().double().abs().max().clamp_min(1e-30))
+    assert rel(out, ref(x)) < 1e-5
+    assert rel(xc.grad, xr.grad) < 1e-4
+    for (k, p), q in zip(m.named_parameters(), ref.parameters()):
+        assert rel(p.grad, q.grad) < 1e-4, k

@@ -161,6 +161,20 @@ def test_low_precision_io(dtype):
     assert np.allclose(f("dD"), gr64["dD"], rtol=1e-3, atol=1e-3 * max(1, np.abs(gr64["dD"]).max()))
 
 
+@pytest.mark.parametrize("N", [17, 40, 64])
+def test_wide_state_spaces(N):
+    """dstate 17 ... 256 (reference: selective_scan.cpp:262) runs as 16-state slices whose outputs add up; checked against the
+    oracle with D, z, delta_bias, softplus and last_state, values and every gradient."""
+    g = make_case(2, 24, N, 70, 2, seed=N, has_z=True)
+    kw = dict(D=g["D"], z=g["z"], delta_bias=g["delta_bias"], delta_softplus=True)
+    out64, last64 = oracle.sscan_fwd(g["u"], g["delta"], g["A"], g["B"], g["C"], precision="f64", **kw)
+    gr64 = oracle.sscan_bwd(g["u"], g["delta"], g["A"], g["B"], g["C"], dout=g["g"], precision="f64", **kw)
+    res = run_cuda(g)
+    assert relerr(res["out"], out64) < 1e-5 and relerr(res["last_state"], last64) < 1e-5
+    for k in ("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias", "dz"):
+        assert relerr(res[k], gr64[k]) < 2e-5, k
+
+
 def test_strided_inputs_and_3d_bc():
     """B/C as strided slices of one projection tensor (MedMamba.py:399,405-406) and the 3-D
     (batch, N, L) form (interface.py:37-42)."""
@@ -188,8 +202,8 @@ def test_errors():
     with pytest.raises(RuntimeError):
         selective_scan_fn(u, u, A, Bm, torch.randn(1, 5, 16, device=dev))
     with pytest.raises(RuntimeError):
-        selective_scan_fn(u, u, torch.randn(8, 17, device=dev), torch.randn(1, 17, 16, device=dev),
-                          torch.randn(1, 17, 16, device=dev))  # dstate > 16 not built
+        selective_scan_fn(u, u, torch.randn(8, 257, device=dev), torch.randn(1, 257, 16, device=dev),
+                          torch.randn(1, 257, 16, device=dev))  # dstate > 256: the reference's limit (selective_scan.cpp:262)
     with pytest.raises(RuntimeError):
         selective_scan_fn(u, u, A, Bm, Bm, D=torch.randn(7, device=dev))
 
