@@ -204,7 +204,9 @@ class ScanProfiler:
                 "achieved": round(top["gbs"], 1), "peak": peak_gbs, "unit": "GB/s",
                 "frac": round(top["gbs"] / peak_gbs, 4), "traffic": traffic,
                 "bytes_per_launch": top["bytes_per_launch"], "ms_per_launch": round(top["ms_per_launch"], 4),
-                "peak_source": peak_src, "formula": "SURVEY.md 8(d) API-boundary bytes, fp32 I/O (s=4)"}
+                "peak_source": peak_src, "formula": "SURVEY.md 8(d) API-boundary bytes, fp32 I/O (s=4)",
+                "timing": "CUDA events around the C-ABI launch in an eager single-stream twin of the same K steps (the kernel alone; in the "
+                          "timed step it shares the GPU with the other branch's kernels)"}
         allscan = {"launches_per_step": round(sum(r["launches"] for r in rows) / steps, 1),
                    "bytes_per_step": tot_bytes / steps, "ms_per_step": round(tot_ms / steps, 4),
                    "achieved": round(tot_bytes / tot_ms / 1e6, 1), "unit": "GB/s",
@@ -472,8 +474,10 @@ def run_cuda(args):
     barrier()
     l0 = _lib.launches()
     prof.enabled = True
+    _models.SS_Conv_SSM.overlap_branches = False   # single stream: each kernel's events bracket that kernel alone, not its co-runners
     for _ in range(args.steps):
         eager_probe(x_dev, y_dev)
+    _models.SS_Conv_SSM.overlap_branches = not args.no_overlap
     prof.enabled = False
     barrier()
     kernel_launches_per_step = (_lib.launches() - l0) // args.steps
