@@ -1,18 +1,16 @@
-# N = 8 A/B of the gradient-synchronisation variants (run under `gpurun --gpus 8`)
-R="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
-run() { name=$1; shift; port=$1; shift
-  timeout 600 $R --master-port $port bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/bench_n8_$name.json 2>> gpurun_out/n8.err
+# N = 1 / 2 / 4 / 8 on one box (run under `gpurun --gpus 8`): the bench lines the driver's scaling run should reproduce
+run() { n=$1; port=$2
+  if [ $n -eq 1 ]; then python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r02_scale_n1.json 2>> gpurun_out/n8.err
+  else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $port bench.py --gpus $n --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r02_scale_n$n.json 2>> gpurun_out/n8.err; fi
   python - <<PY
 import json
 try:
-    d = json.loads(open("gpurun_out/bench_n8_$name.json").read().strip().splitlines()[-1])
-    print("$name", d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"], d["config"]["ddp"][:60])
+    d = json.loads(open("gpurun_out/bench_r02_scale_n$n.json").read().strip().splitlines()[-1])
+    print("N=$n", d["ms_per_step"], d["value"], d["e2e"]["value"])
 except Exception as e:
-    print("$name FAILED", e)
+    print("N=$n FAILED", e)
 PY
 }
 rm -f gpurun_out/n8.err
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n1_ref8.json 2>> gpurun_out/n8.err; python -c "import json;d=json.loads(open('gpurun_out/bench_n1_ref8.json').read().strip().splitlines()[-1]);print('n1', d['ms_per_step'], d['value'], d['e2e']['ms_per_step'])"
-run flat 29521 --ddp-impl flat
-run torch 29522 --ddp-impl torch
-grep -v Warning gpurun_out/n8.err | grep -v "return Variable" | tail -3
+run 1 0; run 2 29531; run 4 29532; run 8 29533
+grep -v Warning gpurun_out/n8.err | grep -v "return Variable" | grep -v "^\*" | tail -3
