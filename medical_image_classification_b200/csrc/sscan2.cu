@@ -1,8 +1,10 @@
-// sscan2.cu -- Mamba-1 selective scan, second-generation forward kernel for sm_100a (fp32 I/O, 16-byte aligned layouts).
+// sscan2.cu -- Mamba-1 selective scan, second-generation forward and backward kernels for sm_100a (fp32 I/O, 16-byte aligned
+// layouts).
 //
-// Same operator and C ABI as sscan.cu (reference selective_scan_fwd_kernel.cuh:67-303 is what it replaces); this file holds
-// the kernels b200_sscan_fwd dispatches to whenever the tensors can be described by TMA tensor maps (fp32, L % 4 == 0,
-// 16-byte aligned strides) -- every launch the SS2D modules make.  Other layouts / 16-bit I/O stay on sscan.cu.
+// Same operator and C ABI as sscan.cu (reference selective_scan_fwd_kernel.cuh:67-303 and selective_scan_bwd_kernel.cuh:75-489
+// are what they replace); this file holds the kernels b200_sscan_fwd / b200_sscan_bwd dispatch to whenever the tensors can be
+// described by TMA tensor maps (fp32, L % 4 == 0, 16-byte aligned strides) -- every launch the SS2D modules make.  Other layouts /
+// 16-bit I/O stay on sscan.cu.  Measurements, pipe-level analysis and the A/B history: DESIGN.md 3.1, profiles/ncu_sscan_r02.md.
 //
 // Why a second design: ncu on the first one (profiles/ncu_sscan_r01.md) showed 5.8 warp-instructions and ~1.7 LSU wavefronts
 // per (row, step) element against a floor of 1.5 / 0.3 -- the MUFU pipe (16 ex2 per element) should be the only limit.
