@@ -185,6 +185,11 @@ class TrainStep:
         if self.dev.type != "cuda":
             raise RuntimeError("TrainStep runs on CUDA modules only: the B200 path has no CPU fallback")
         self.autocast = autocast
+        # the models issue their two branches on two streams on purpose (models.SS_Conv_SSM): the engine's advisory about
+        # AccumulateGrad nodes created on another stream than the gradient's producer does not apply (it synchronises them itself)
+        _quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if _quiet is not None:
+            _quiet(False)
         self.use_graph = bool(graph)
         self.ddp = bool(ddp)
         self.loss_fn = loss_fn or torch.nn.functional.cross_entropy
