@@ -273,9 +273,9 @@ constexpr float kLn2 = 0.6931471805599453f;
 #define B200_BWD_REGS 168   // 3 warps per SM sub-partition (16 K registers each): 12 per SM, one wave at the stage-0 shape
 #endif
 #ifndef B200_BWD_PRIV
-#define B200_BWD_PRIV 2
+#define B200_BWD_PRIV 3     // A/B over the ten scan calls of a MedMamba-T step (tools/dbg_variants.sh, two runs each): 2 -> 5.37 ms, 3 -> 5.29 ms
 #endif
-constexpr int PRIV_SLOTS = B200_BWD_PRIV;   // 1: dA in shared memory; 2: dA and the adjoint carry
+constexpr int PRIV_SLOTS = B200_BWD_PRIV;   // 1: dA in shared memory; 2: dA and the adjoint carry; 3: and A log2(e) (fewest spills)
 
 struct BwdMaps {
     CUtensorMap u, delta, dout, B, C;   // loads
