@@ -236,7 +236,7 @@ typedef struct {
     b200_ssd_fwd_params f;  /* forward inputs + its workspace (f.out / f.final_states unused) */
     int64_t dout_stride[4];
     const void* dout;
-    /* gradients: contiguous fp32 in the logical shapes of their primals, written (not accumulated)
+    /* gradients: fp32 in the logical shapes of their primals (strides below), written (not accumulated)
        except the three reduced over batch/sequence, which the caller zero-fills */
     float* dx;       /* (batch, L, H, P) */
     float* ddt;      /* (batch, L, H) */
@@ -246,6 +246,13 @@ typedef struct {
     float* dD;       /* (H) or NULL, accumulated */
     float* ddt_bias; /* (H) or NULL, accumulated */
     float* scratch;  /* b200_ssd_bwd_scratch_bytes() bytes */
+    /* element strides of dx (batch, L, head, p), ddt (batch, L, head), dB / dC (batch, L, group, n).  All zero = contiguous in
+       the logical shape.  The models pass the strides of the primals (sequence-contiguous views, SSD/MedSSD.py:344-347), so the
+       gradients come back in the layout the cross-scan adjoint reads and no strided copy follows. */
+    int64_t dx_stride[4];
+    int64_t ddt_stride[3];
+    int64_t dB_stride[4];
+    int64_t dC_stride[4];
 } b200_ssd_bwd_params;
 
 size_t b200_ssd_workspace_bytes(int32_t batch, int32_t seqlen, int32_t nheads, int32_t headdim,

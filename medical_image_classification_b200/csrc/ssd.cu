@@ -76,6 +76,18 @@ struct View4 {
 };
 template <typename T> static View4<T> view4(const void* p, const int64_t* s) { return View4<T>{(const T*)p, s[0], s[1], s[2], s[3]}; }
 
+// element strides of a gradient output (batch, L, head | group, p | n): the backward writes every gradient in the layout the caller
+// asks for -- the layout of its primal in the models (sequence-contiguous channel-major storage), so no strided copy follows and
+// the epilogue stores of a warp (32 consecutive sequence positions, one column) are contiguous
+struct OutS {
+    int64_t s0, s1, s2, s3;
+    __device__ __forceinline__ size_t at(int b, int l, int h, int p) const { return (size_t)(b * s0 + (int64_t)l * s1 + h * s2 + p * s3); }
+};
+static OutS outs_of(const int64_t* s, int64_t d1, int64_t d2, int64_t d3) {   // all-zero strides = contiguous (batch, L, d2, d3)
+    if (s[0] == 0 && s[1] == 0 && s[2] == 0 && s[3] == 0) return OutS{d1 * d2 * d3, d2 * d3, d3, 1};
+    return OutS{s[0], s[1], s[2], s[3]};
+}
+
 // ---- tensor-core tile engine -----------------------------------------------------------------
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
     uint32_t r;
@@ -971,7 +983,7 @@ __global__ void __launch_bounds__(NTHR) state_pass_bwd_kernel_scalar(Dims d, Ws 
 //          ddtp_exp[s] = sum_p x Z;  dcs_pos[l] = sum_p dout (out - D x);  dD += sum dout x --------
 template <typename T>
 __global__ void __launch_bounds__(NTHR, 2) dx_kernel(View4<T> X, View4<T> Bv, View4<T> DO, View4<T> OUT, const float* D, Dims d, Ws ws,
-                                                     const float* G, float* dx, float* ddtp_exp, float* dcs_pos, float* dD, int x3) {
+                                                     const float* G, float* dx, OutS dxs, float* ddtp_exp, float* dcs_pos, float* dD, int x3) {
     Smem& sm = smem_ref();
     const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
     int bid = blockIdx.x;
@@ -1036,7 +1048,7 @@ __global__ void __launch_bounds__(NTHR, 2) dx_kernel(View4<T> X, View4<T> Bv, Vi
                 if (s < q && p < d.P) {
                     const float z = acc.v[mi][ni][r];
                     const float xv = X.at(b, l0 + s, h, p), dv = DO.at(b, l0 + s, h, p), ov = OUT.at(b, l0 + s, h, p);
-                    dx[(((size_t)b * d.L + l0 + s) * d.H + h) * d.P + p] = sm.dtp[0][s] * z + Dh * dv;
+                    dx[dxs.at(b, l0 + s, h, p)] = sm.dtp[0][s] * z + Dh * dv;
                     r1[mi][r >> 1] += xv * z;
                     r2[mi][r >> 1] += dv * (ov - Dh * xv);
                     dDl += dv * xv;
@@ -1066,7 +1078,7 @@ __global__ void __launch_bounds__(NTHR, 2) dx_kernel(View4<T> X, View4<T> Bv, Vi
 // allows) into UMMA tiles, accumulator row = one thread in the epilogue (row sums need no shuffles).
 template <typename T>
 __global__ void __launch_bounds__(NTHR, TcEngine::MIN_CTAS) dx_kernel_tc(View4<T> X, View4<T> Bv, View4<T> DO, View4<T> OUT, const float* D, Dims d, Ws ws,
-                                                        const float* G, float* dx, float* ddtp_exp, float* dcs_pos, float* dD, int x3) {
+                                                        const float* G, float* dx, OutS dxs, float* ddtp_exp, float* dcs_pos, float* dD, int x3) {
     using E = TcEngine;
     E::Shared& sm = E::smem();
     const int ntm = (d.Q + BM - 1) / BM, ntp = (d.P + BN - 1) / BN;
@@ -1126,7 +1138,7 @@ __global__ void __launch_bounds__(NTHR, TcEngine::MIN_CTAS) dx_kernel_tc(View4<T
         srow = sidx;
         if (sidx < q && pp < d.P) {
             const float xv = X.at(b, l0 + sidx, h, pp), dv = DO.at(b, l0 + sidx, h, pp), ov = OUT.at(b, l0 + sidx, h, pp);
-            dx[(((size_t)b * d.L + l0 + sidx) * d.H + h) * d.P + pp] = sm.dtp[0][sidx] * z + Dh * dv;
+            dx[dxs.at(b, l0 + sidx, h, pp)] = sm.dtp[0][sidx] * z + Dh * dv;
             r1 += xv * z;
             r2 += dv * (ov - Dh * xv);
             dDl += dv * xv;
@@ -1203,7 +1215,7 @@ __global__ void __launch_bounds__(NTHR, 2) dcb_kernel(View4<T> X, View4<T> DO, D
 // ---- B5: dC = dCB B + sum_h exp(cs_h) dout_h Sin_h ;  dB = dCB^T C + sum_h exp(cs_Q - cs) dt' x_h G_h ----
 template <typename T>
 __global__ void __launch_bounds__(NTHR, 2) dbc_kernel(View4<T> X, View4<T> Bv, View4<T> Cv, View4<T> DO, Dims d, Ws ws,
-                                                      const float* dcb_all, const float* G, float* dB, float* dC, int x3) {
+                                                      const float* dcb_all, const float* G, float* dB, float* dC, OutS dbs, OutS dcs, int x3) {
     Smem& sm = smem_ref();
     const int ntm = (d.Q + BM - 1) / BM, ntn = (d.N + BN - 1) / BN;
     int bid = blockIdx.x;
@@ -1278,16 +1290,17 @@ __global__ void __launch_bounds__(NTHR, 2) dbc_kernel(View4<T> X, View4<T> Bv, V
         }
     }
     float* o = which == 0 ? dC : dB;
+    const OutS os = which == 0 ? dcs : dbs;
     for_each_acc(acc, [&](int m, int n, float& v) {
         const int l = m0 + m, nn = n0 + n;
-        if (l < q && nn < d.N) o[(((size_t)b * d.L + l0 + l) * d.G + g) * d.N + nn] = v;
+        if (l < q && nn < d.N) o[os.at(b, l0 + l, g, nn)] = v;
     });
 }
 
 // B5 on the tcgen05 engine.
 template <typename T>
 __global__ void __launch_bounds__(NTHR, TcEngine::MIN_CTAS) dbc_kernel_tc(View4<T> X, View4<T> Bv, View4<T> Cv, View4<T> DO, Dims d, Ws ws,
-                                                         const float* dcb_all, const float* G, float* dB, float* dC, int x3) {
+                                                         const float* dcb_all, const float* G, float* dB, float* dC, OutS dbs, OutS dcs, int x3) {
     using E = TcEngine;
     E::Shared& sm = E::smem();
     const int ntm = (d.Q + BM - 1) / BM, ntn = (d.N + BN - 1) / BN;
@@ -1359,9 +1372,10 @@ __global__ void __launch_bounds__(NTHR, TcEngine::MIN_CTAS) dbc_kernel_tc(View4<
         }
     }
     float* o = which == 0 ? dC : dB;
+    const OutS os = which == 0 ? dcs : dbs;
     eng.for_each(sm, [&](int m, int n, float& v) {
         const int l = m0 + m, nn = n0 + n;
-        if (l < q && nn < d.N) o[(((size_t)b * d.L + l0 + l) * d.G + g) * d.N + nn] = v;
+        if (l < q && nn < d.N) o[os.at(b, l0 + l, g, nn)] = v;
     });
     eng.end(sm);
 }
@@ -1370,7 +1384,7 @@ __global__ void __launch_bounds__(NTHR, TcEngine::MIN_CTAS) dbc_kernel_tc(View4<
 template <typename T>
 __global__ void __launch_bounds__(MAXQ) dt_bwd_kernel(const T* dt, int64_t s0, int64_t s1, int64_t s2, const float* A,
                                                       const float* dt_bias, int softplus, float dt_min, float dt_max, Dims d, Ws ws,
-                                                      const float* ddtp_exp, const float* dcs_pos, const float* dcsQ, float* ddt,
+                                                      const float* ddtp_exp, const float* dcs_pos, const float* dcsQ, float* ddt, OutS dts,
                                                       float* dA, float* ddt_bias) {
     __shared__ float wsum[MAXQ / 32];
     __shared__ float red[2][MAXQ / 32];
@@ -1406,7 +1420,7 @@ __global__ void __launch_bounds__(MAXQ) dt_bwd_kernel(const T* dt, int64_t s0, i
         }
         if (v < dt_min || v > dt_max) dv = 0.f;
         g = ddtp * dv;
-        ddt[((size_t)b * d.L + l) * d.H + h] = g;
+        ddt[dts.at(b, l, h, 0)] = g;
     } else {
         dAl = 0.f;
     }
@@ -1605,6 +1619,9 @@ static int bwd_impl(const b200_ssd_bwd_params* q, cudaStream_t st) {
     const size_t SM = sizeof(Smem);
     const int ntq128 = (d.Q + BM - 1) / BM, ntq64 = (d.Q + BN - 1) / BN;
     const int ntn128 = (d.N + BM - 1) / BM, ntn64 = (d.N + BN - 1) / BN, ntp64 = (d.P + BN - 1) / BN;
+    const OutS dxs = outs_of(q->dx_stride, d.L, d.H, d.P), dbs = outs_of(q->dB_stride, d.L, d.G, d.N), dcs = outs_of(q->dC_stride, d.L, d.G, d.N);
+    const int64_t dt3[4] = {q->ddt_stride[0], q->ddt_stride[1], q->ddt_stride[2], 0};
+    const OutS dts = outs_of(dt3, d.L, d.H, 1);
     const cudaError_t e = cudaMemsetAsync(sc.ddtp_exp, 0, scratch_zero_floats(d) * sizeof(float), st);
     if (e != cudaSuccess) {
         set_error("b200_ssd_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
@@ -1630,19 +1647,19 @@ static int bwd_impl(const b200_ssd_bwd_params* q, cudaStream_t st) {
     }
     if (use_tcgen05())
         LAUNCH((dx_kernel_tc<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, (x3 ? tc::SMEM_X3 : tc::SMEM_TF32), st, X, Bv, DO, OUT, p->D,
-               d, ws, sc.dstates, q->dx, sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
+               d, ws, sc.dstates, q->dx, dxs, sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
     else
-        LAUNCH((dx_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Bv, DO, OUT, p->D, d, ws, sc.dstates, q->dx,
+        LAUNCH((dx_kernel<T>), (size_t)d.batch * d.nc * d.H * ntq128 * ntp64, NTHR, SM, st, X, Bv, DO, OUT, p->D, d, ws, sc.dstates, q->dx, dxs,
                sc.ddtp_exp, sc.dcs_pos, q->dD, x3);
     LAUNCH((dcb_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntq64, NTHR, SM, st, X, DO, d, ws, sc.dcb, x3);
     if (use_tcgen05())
         LAUNCH((dbc_kernel_tc<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntn64 * 2, NTHR, (x3 ? tc::SMEM_X3 : tc::SMEM_TF32), st, X, Bv, Cv, DO, d,
-               ws, sc.dcb, sc.dstates, q->dB, q->dC, x3);
+               ws, sc.dcb, sc.dstates, q->dB, q->dC, dbs, dcs, x3);
     else
         LAUNCH((dbc_kernel<T>), (size_t)d.batch * d.nc * d.G * ntq128 * ntn64 * 2, NTHR, SM, st, X, Bv, Cv, DO, d, ws, sc.dcb, sc.dstates,
-               q->dB, q->dC, x3);
+               q->dB, q->dC, dbs, dcs, x3);
     LAUNCH((dt_bwd_kernel<T>), (size_t)d.batch * d.H * d.nc, d.Q, 0, st, (const T*)p->dt, p->dt_stride[0], p->dt_stride[1],
-           p->dt_stride[2], p->A, p->dt_bias, p->dt_softplus, p->dt_min, p->dt_max, d, ws, sc.ddtp_exp, sc.dcs_pos, sc.dcsQ, q->ddt,
+           p->dt_stride[2], p->A, p->dt_bias, p->dt_softplus, p->dt_min, p->dt_max, d, ws, sc.ddtp_exp, sc.dcs_pos, sc.dcsQ, q->ddt, dts,
            q->dA, q->ddt_bias);
     return 0;
 }

@@ -80,6 +80,17 @@ def _f32c(t):
     return None if t is None else t.detach().to(torch.float32).contiguous()
 
 
+def _empty_like_layout(t):
+    """fp32 tensor of t's shape with t's strides when t is dense (any dimension order), contiguous otherwise."""
+    expect, dense = 1, True
+    for size, stride in sorted(((sz, st) for sz, st in zip(t.shape, t.stride()) if sz != 1), key=lambda e: e[1]):
+        dense = dense and stride == expect
+        expect *= size
+    if dense and all(st > 0 for sz, st in zip(t.shape, t.stride()) if sz != 1):
+        return torch.empty_strided(t.shape, t.stride(), dtype=torch.float32, device=t.device)
+    return torch.empty(t.shape, dtype=torch.float32, device=t.device)
+
+
 class SsdChunkScanFn(torch.autograd.Function):
     @staticmethod
     @_no_autocast
@@ -123,10 +134,9 @@ class SsdChunkScanFn(torch.autograd.Function):
         G, N = B_.shape[2], B_.shape[3]
         dev = x.device
         dout = dout.to(x.dtype)
-        dx = torch.empty((batch, L, H, P), dtype=torch.float32, device=dev)
-        ddt = torch.empty((batch, L, H), dtype=torch.float32, device=dev)
-        dB = torch.empty((batch, L, G, N), dtype=torch.float32, device=dev)
-        dC = torch.empty((batch, L, G, N), dtype=torch.float32, device=dev)
+        # every gradient in the layout of its primal (the models pass sequence-contiguous views of channel-major storage,
+        # SSD/MedSSD.py:344-347): the cross-scan adjoint then reads them in place -- no strided copy after the kernels
+        dx, ddt, dB, dC = (_empty_like_layout(t) for t in (x, dt_, B_, C_))
         dA = torch.zeros(H, dtype=torch.float32, device=dev)
         dD = torch.zeros(H, dtype=torch.float32, device=dev) if D32 is not None else None
         dbias = torch.zeros(H, dtype=torch.float32, device=dev) if bias32 is not None else None
@@ -138,6 +148,8 @@ class SsdChunkScanFn(torch.autograd.Function):
         q.f.out, q.f.workspace = out.data_ptr(), ws.data_ptr()
         q.dout_stride[:] = list(dout.stride())
         q.dout, q.dx, q.ddt, q.dB, q.dC = dout.data_ptr(), dx.data_ptr(), ddt.data_ptr(), dB.data_ptr(), dC.data_ptr()
+        q.dx_stride[:], q.ddt_stride[:] = list(dx.stride()), list(ddt.stride())
+        q.dB_stride[:], q.dC_stride[:] = list(dB.stride()), list(dC.stride())
         q.dA, q.dD, q.ddt_bias, q.scratch = dA.data_ptr(), _lib.ptr(dD), _lib.ptr(dbias), scratch.data_ptr()
         prof = _profiler
         with torch.cuda.device(dev):
