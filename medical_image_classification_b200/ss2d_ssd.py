@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .cross import cross_scan4, ssd_merge4
+from .cross import cross_scan4_split, ssd_merge4
 from .ss2d import DwConvSiluFn
 from .ssd_combined import RMSNormGated, mamba_chunk_scan_combined
 
@@ -88,7 +88,7 @@ class SS2D_with_SSD(nn.Module):
         # cross-scan of x, B, C and dt (SSD/MedSSD.py:332-336)
         gn = self.ngroups * self.d_state
         # one pass per component (csrc/cross.cu::cross_scan4_kernel), channel slices read in place
-        xs, Bs, Cs, dts = (cross_scan4(t) for t in torch.split(xBCdt, [self.d_ssm, gn, gn, self.nheads], dim=1))
+        xs, Bs, Cs, dts = cross_scan4_split(xBCdt, (self.d_ssm, gn, gn, self.nheads))   # one node: its backward fills one gradient tensor
         # (b, l, k*d) views with L stride 1 -- never made contiguous (SSD/MedSSD.py:344-347)
         xs = xs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (-1, self.headdim))     # (B, L, 4*nheads, P)
         Bs = Bs.float().reshape(B, -1, L).permute(0, 2, 1).unflatten(2, (self.ngroups, -1))     # (B, L, G, 4*N)
