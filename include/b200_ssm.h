@@ -324,6 +324,12 @@ int b200_shuffle_cat_add_fwd(const void* left, int32_t left_channels_last, const
 int b200_shuffle_cat_add_bwd(const void* dout, int32_t io_dtype, void* dleft, int32_t left_channels_last, void* dx, int32_t lx_dtype,
                              int32_t B, int32_t c, int32_t P, b200_stream_t stream);
 
+/* PatchMerging2D gather (reference MedMamba.py:186-204, `x0..x3 = x[:, i::2, j::2, :]`, `torch.cat`): x (batch, H, W, C) ->
+ * out (batch, H/2, W/2, 4 C), out[b, h2, w2, k C + c] = x[b, 2 h2 + (k & 1), 2 w2 + (k >> 1), c]; pixel_bytes = C * element size,
+ * a multiple of 16.  inverse != 0: the adjoint, x = d out (batch, H/2, W/2, 4 C) -> out = d x (batch, H, W, C). */
+int b200_patch_merge(const void* x, void* out, int32_t batch, int32_t H, int32_t W, int32_t pixel_bytes, int32_t inverse,
+                     b200_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------ */
 const char* b200_last_error(void);   /* thread-local message of the last failing call */
 int b200_version(void);              /* ABI version, bumped on any struct change */

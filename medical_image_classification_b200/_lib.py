@@ -84,7 +84,7 @@ EXPORTS = [
     "b200_cross_scan_pack_strided", "b200_cross_scan_unpack4", "b200_atrous_scan", "b200_atrous_merge",
     "b200_ln_gate_grid", "b200_ln_gate_fwd", "b200_ln_gate_bwd",
     "b200_dwconv_silu_fwd", "b200_dwconv_silu_bwd",
-    "b200_shuffle_cat_add_fwd", "b200_shuffle_cat_add_bwd",
+    "b200_shuffle_cat_add_fwd", "b200_shuffle_cat_add_bwd", "b200_patch_merge",
     "b200_last_error", "b200_version", "b200_kernel_launches", "b200_sizeof_params",
 ]
 
@@ -134,6 +134,7 @@ def load() -> C.CDLL:
     lib.b200_dwconv_silu_bwd.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_shuffle_cat_add_fwd.argtypes = [vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, vp]
     lib.b200_shuffle_cat_add_bwd.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp]
+    lib.b200_patch_merge.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200_atrous_scan.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200_atrous_merge.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     lib.b200_cross_scan_pack_strided.argtypes = [vp, vp, i64, i64, i64, i32, i32, i32, i32, vp]

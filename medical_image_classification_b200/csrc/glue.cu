@@ -124,6 +124,57 @@ static int glue_bwd(const void* dout, void* dleft, int cl, void* dx, int B, int 
     return check_launch("shuffle_cat_add_bwd_kernel");
 }
 
+// ---- PatchMerging2D gather (reference MedMamba.py:186-204): x (B, H, W, C) -> out (B, H/2, W/2, 4 C) with
+//      out[b, h2, w2, k C + c] = x[b, 2 h2 + (k & 1), 2 w2 + (k >> 1), c]   (x0 | x1 | x2 | x3 = (0,0) (1,0) (0,1) (1,1)),
+//      rows / columns beyond 2 (H/2), 2 (W/2) dropped as the reference does.  A pure permutation of 16-byte units (C elements of
+//      any dtype per pixel, C * size % 16 == 0): one pass instead of four strided slice copies + cat; the backward is the inverse
+//      permutation (every input pixel feeds exactly one output slot; dropped rows / columns get zero). ----
+__global__ void __launch_bounds__(256) patch_merge_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int H, int W, int upp, int64_t total,
+                                                          int inverse) {
+    // upp: 16-byte units per input pixel.  forward: one thread per OUTPUT unit; inverse: one thread per INPUT unit (of dx)
+    const int H2 = H >> 1, W2 = W >> 1;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        if (!inverse) {
+            const int u = (int)(idx % upp);
+            int64_t r = idx / upp;
+            const int k = (int)(r & 3); r >>= 2;
+            const int w2 = (int)(r % W2); r /= W2;
+            const int h2 = (int)(r % H2);
+            const int64_t b = r / H2;
+            out[idx] = __ldcs(x + ((b * H + 2 * h2 + (k & 1)) * W + 2 * w2 + (k >> 1)) * upp + u);
+        } else {   // x = d out (B, H2, W2, 4 C), out = d x (B, H, W, C)
+            const int u = (int)(idx % upp);
+            int64_t r = idx / upp;
+            const int w = (int)(r % W); r /= W;
+            const int h = (int)(r % H);
+            const int64_t b = r / H;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if ((h >> 1) < H2 && (w >> 1) < W2) {
+                const int k = (h & 1) + 2 * (w & 1);
+                v = __ldcs(x + (((b * H2 + (h >> 1)) * W2 + (w >> 1)) * 4 + k) * upp + u);
+            }
+            out[idx] = v;
+        }
+    }
+}
+
+}  // namespace b200
+
+extern "C" int b200_patch_merge(const void* x, void* out, int32_t batch, int32_t H, int32_t W, int32_t pixel_bytes, int32_t inverse,
+                                b200_stream_t stream) {
+    using namespace b200;
+    B200_REQUIRE(x && out && batch > 0 && H >= 2 && W >= 2 && pixel_bytes > 0 && pixel_bytes % 16 == 0,
+                 "b200_patch_merge: need H, W >= 2 and a pixel size that is a multiple of 16 bytes (got %d)", pixel_bytes);
+    B200_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "b200_patch_merge: 16-byte aligned tensors");
+    const int upp = pixel_bytes / 16;
+    const int64_t total = inverse ? (int64_t)batch * H * W * upp : (int64_t)batch * (H / 2) * (W / 2) * 4 * upp;
+    const int64_t want = (total + 255) / 256;
+    const unsigned grid = (unsigned)(want < 148 * 16 ? (want < 1 ? 1 : want) : 148 * 16);
+    patch_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, H, W, upp, total, inverse);
+    return check_launch("patch_merge_kernel");
+}
+
+namespace b200 {
 }  // namespace b200
 
 using namespace b200;

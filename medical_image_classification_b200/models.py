@@ -61,6 +61,37 @@ class PatchEmbed2D(nn.Module):
         return _layer_norm(x, self.norm)
 
 
+class PatchMergeGatherFn(torch.autograd.Function):
+    """The 2x2 gather of PatchMerging2D (`x0..x3 = x[:, i::2, j::2, :]`, `torch.cat`, MedMamba.py:186-204) in one pass; the backward is
+    the inverse permutation (csrc/glue.cu::patch_merge_kernel)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import _lib
+        _lib.require_cuda(x)
+        lib = _lib.load()
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        out = torch.empty((B, H // 2, W // 2, 4 * C), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.b200_patch_merge(x.data_ptr(), out.data_ptr(), B, H, W, C * x.element_size(), 0, _lib.stream_ptr(x.device)),
+                       "b200_patch_merge")
+        ctx.shape = (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import _lib
+        lib = _lib.load()
+        B, H, W, C = ctx.shape
+        dout = dout.contiguous()
+        dx = torch.empty((B, H, W, C), dtype=dout.dtype, device=dout.device)
+        with torch.cuda.device(dout.device):
+            _lib.check(lib.b200_patch_merge(dout.data_ptr(), dx.data_ptr(), B, H, W, C * dout.element_size(), 1, _lib.stream_ptr(dout.device)),
+                       "b200_patch_merge")
+        return dx
+
+
 class PatchMerging2D(nn.Module):
     """2x2 patch merge: (B, H, W, C) -> (B, H/2, W/2, 2C)."""
 
@@ -73,8 +104,11 @@ class PatchMerging2D(nn.Module):
     def forward(self, x):
         B, H, W, C = x.shape
         h2, w2 = H // 2, W // 2
-        parts = [x[:, i::2, j::2, :][:, :h2, :w2, :] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))]
-        x = torch.cat(parts, dim=-1)
+        if (C * x.element_size()) % 16 == 0 and h2 > 0 and w2 > 0:
+            x = PatchMergeGatherFn.apply(x)                # one gather pass (csrc/glue.cu)
+        else:
+            parts = [x[:, i::2, j::2, :][:, :h2, :w2, :] for (i, j) in ((0, 0), (1, 0), (0, 1), (1, 1))]
+            x = torch.cat(parts, dim=-1)
         return self.reduction(_layer_norm(x, self.norm))
 
 
@@ -178,9 +212,11 @@ class SS_Conv_SSM(nn.Module):
         return self.conv33conv33conv11(left)
 
     def forward(self, input):
+        from . import _lib
+        _lib.require_cuda(input)                           # no CPU path: oracle/cpu_path.py holds the eager CPU tree
         left, right = split_halves(input)
         side = None
-        if self.overlap_branches and input.is_cuda:
+        if self.overlap_branches:
             cur = torch.cuda.current_stream(input.device)
             side = branch_stream(input.device)
             side.wait_stream(cur)                          # fork: `left` is ready on the caller's stream
