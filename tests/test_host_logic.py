@@ -67,3 +67,32 @@ def test_rows_by_batch_layout_views():
     x2 = torch.arange(2 * D * B * L, dtype=torch.float32).view(2, D, B, L)
     u4 = x2.permute(2, 0, 1, 3)
     assert u4.stride() == (L, D * B * L, B * L, 1)
+
+
+def test_dense_layout_helpers():
+    """train_step._dense / ssd_combined._empty_like_layout: any dimension order of a dense tensor is recognised (channels_last
+    parameters, the models' sequence-contiguous views), gaps and overlaps are not."""
+    from medical_image_classification_b200.ssd_combined import _empty_like_layout
+    from medical_image_classification_b200.train_step import _dense
+    a = torch.empty(4, 6, 5, 3)
+    assert _dense(a) and _dense(a.permute(0, 2, 3, 1)) and _dense(a.contiguous(memory_format=torch.channels_last))
+    assert not _dense(a[:, :3]) and not _dense(a.expand(2, 4, 6, 5, 3)[0].expand(4, 6, 5, 3)[:, ::2])
+    assert _dense(torch.empty(1, 7, 1, 3).permute(2, 0, 3, 1))          # size-1 dimensions carry any stride
+    view = torch.empty(2, 8, 10).permute(0, 2, 1).unflatten(2, (2, 4))  # (b, l, h, p) view of channel-major storage
+    g = _empty_like_layout(view)
+    assert g.shape == view.shape and g.stride() == view.stride() and g.dtype == torch.float32
+    sliced = torch.empty(2, 10, 2, 8)[..., :4]                          # not dense: falls back to a contiguous tensor
+    g2 = _empty_like_layout(sliced)
+    assert g2.shape == sliced.shape and g2.is_contiguous()
+
+
+def test_chunk_size_mapping_and_wide_state_slices_are_host_side():
+    """mamba_chunk_scan_combined maps any chunk_size to a tiled length and selective_scan_fn slices wide state spaces before any
+    kernel call: both raise the no-CPU-path error (not a shape error) on CPU tensors."""
+    import pytest
+    from medical_image_classification_b200.selective_scan_interface import MAX_DSTATE, selective_scan_fn
+    u = torch.randn(1, 4, 8)
+    with pytest.raises(RuntimeError, match="dstate"):
+        selective_scan_fn(u, u, torch.randn(4, MAX_DSTATE + 1), torch.randn(1, MAX_DSTATE + 1, 8), torch.randn(1, MAX_DSTATE + 1, 8))
+    with pytest.raises(RuntimeError):   # 40 states: sliced, then the first slice hits require_cuda
+        selective_scan_fn(u, u, torch.randn(4, 40), torch.randn(1, 40, 8), torch.randn(1, 40, 8))
